@@ -1,0 +1,272 @@
+"""ctypes binding of include/rustyread_b200.h (the drop-in boundary for src/simulate/mod.rs:172-186)."""
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import _build
+
+u8p = C.POINTER(C.c_uint8)
+u32p = C.POINTER(C.c_uint32)
+u64p = C.POINTER(C.c_uint64)
+f64p = C.POINTER(C.c_double)
+
+RR_REAL, RR_JUNK, RR_RANDOM = 0, 1, 2
+RR_PLUS, RR_MINUS, RR_NOSTRAND = 0, 1, 2
+
+# numpy mirror of struct rr_desc (80 bytes)
+DESC_DTYPE = np.dtype([
+    ("type", "<u4"), ("ref_idx", "<u4"), ("strand", "<u4"), ("has_chimera", "<u4"),
+    ("ctype", "<u4"), ("cref_idx", "<u4"), ("cstrand", "<u4"), ("reserved", "<u4"),
+    ("start", "<u8"), ("end", "<u8"), ("cstart", "<u8"), ("cend", "<u8"),
+    ("identity", "<f8"), ("seed", "<u8"),
+])
+
+
+class rr_batch(C.Structure):
+    _fields_ = [("n_reads", C.c_uint64), ("offsets", u64p), ("lengths", u64p), ("seq", u8p), ("qual", u8p),
+                ("real_identity", f64p), ("total_bytes", C.c_uint64), ("total_bases", C.c_uint64), ("k", C.c_uint32)]
+
+
+class RRError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__("rustyread_b200 error %d: %s" % (code, msg))
+        self.code = code
+
+
+EXPORTS = {
+    "rr_create": (C.c_int, [C.c_int, C.POINTER(C.c_void_p)]),
+    "rr_destroy": (None, [C.c_void_p]),
+    "rr_last_error": (C.c_char_p, [C.c_void_p]),
+    "rr_device_count": (C.c_int, []),
+    "rr_set_references": (C.c_int, [C.c_void_p, C.c_uint64, C.POINTER(C.c_void_p), u64p, C.c_void_p]),
+    "rr_set_error_model": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "rr_set_qscore_model": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "rr_set_adapter": (C.c_int, [C.c_void_p, C.c_char_p, C.c_uint64, C.c_char_p, C.c_uint64, C.c_double, C.c_double, C.c_double, C.c_double]),
+    "rr_set_glitch": (C.c_int, [C.c_void_p, C.c_double, C.c_double, C.c_double]),
+    "rr_generate": (C.c_int, [C.c_void_p, C.c_uint64, C.c_void_p, C.POINTER(rr_batch)]),
+    "rr_upload": (C.c_int, [C.c_void_p, C.c_uint64, C.c_void_p]),
+    "rr_run": (C.c_int, [C.c_void_p]),
+    "rr_download": (C.c_int, [C.c_void_p, C.POINTER(rr_batch)]),
+    "rr_kernel_launches": (C.c_uint64, [C.c_void_p]),
+    "rr_last_run_ms": (C.c_int, [C.c_void_p, C.POINTER(C.c_float)]),
+    "rr_last_run_bases": (C.c_uint64, [C.c_void_p]),
+    "rr_stream": (C.c_void_p, [C.c_void_p]),
+    "rr_debug_align": (C.c_int, [C.c_void_p, C.c_char_p, C.c_uint32, C.c_char_p, C.c_uint32, C.c_void_p, u32p, u32p]),
+    "rr_debug_rng_words": (C.c_int, [C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint32, C.c_void_p]),
+    "rr_debug_fetch": (C.c_int, [C.c_void_p, C.c_uint64, C.c_int, C.c_void_p, C.c_uint64, u64p]),
+}
+
+
+class Library:
+    """The loaded C-ABI library.  Loading never falls back to anything else."""
+
+    def __init__(self, path=None):
+        self.path = path or _build.LIB
+        if not os.path.exists(self.path):
+            raise RRError(1, "CUDA library %s is missing: run __graft_entry__.build() (no CPU fallback exists)" % self.path)
+        self.dll = C.CDLL(self.path)
+        for name, (res, args) in EXPORTS.items():
+            fn = getattr(self.dll, name)  # AttributeError if the library does not export a declared symbol
+            fn.restype = res
+            fn.argtypes = args
+
+    def device_count(self):
+        return self.dll.rr_device_count()
+
+
+_lib = None
+
+
+def load_library(path=None):
+    global _lib
+    if _lib is None or (path and _lib.path != path):
+        _lib = Library(path)
+    return _lib
+
+
+class Batch:
+    """Host view of one generated batch (numpy views over the library's pinned buffers)."""
+
+    def __init__(self, b):
+        n = int(b.n_reads)
+        self.n = n
+        self.k = int(b.k)
+        self.total_bytes = int(b.total_bytes)
+        self.total_bases = int(b.total_bases)
+        self.offsets = np.ctypeslib.as_array(b.offsets, shape=(n + 1,))
+        self.lengths = np.ctypeslib.as_array(b.lengths, shape=(n,))
+        self.real_identity = np.ctypeslib.as_array(b.real_identity, shape=(n,))
+        tb = max(1, self.total_bytes)
+        self.seq = np.ctypeslib.as_array(b.seq, shape=(tb,))
+        self.qual = np.ctypeslib.as_array(b.qual, shape=(tb,))
+
+    def read(self, i):
+        o, l = int(self.offsets[i]), int(self.lengths[i])
+        return bytes(self.seq[o:o + l]), bytes(self.qual[o:o + l])
+
+
+class Context:
+    """Host-side mirror of the reference objects `generate_read` borrows (src/simulate/mod.rs:223-231)."""
+
+    def __init__(self, device=0, lib=None):
+        self.lib = lib or load_library()
+        h = C.c_void_p()
+        rc = self.lib.dll.rr_create(device, C.byref(h))
+        if rc:
+            raise RRError(rc, self.lib.dll.rr_last_error(None).decode())
+        self.h = h
+        self.k = None
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.dll.rr_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _ck(self, rc):
+        if rc:
+            raise RRError(rc, self.lib.dll.rr_last_error(self.h).decode())
+
+    # -- immutable inputs ---------------------------------------------------------------
+    def set_references(self, seqs, circular=None):
+        """seqs: list of bytes (References::sequences[i].seq); circular: list of bool."""
+        n = len(seqs)
+        keep = [np.frombuffer(s, dtype=np.uint8) if len(s) else np.zeros(1, np.uint8) for s in seqs]
+        ptrs = (C.c_void_p * n)(*[a.ctypes.data for a in keep])
+        lens = (C.c_uint64 * n)(*[len(s) for s in seqs])
+        circ = (C.c_uint8 * n)(*[1 if (circular and circular[i]) else 0 for i in range(n)])
+        self._ck(self.lib.dll.rr_set_references(self.h, n, ptrs, lens, circ))
+
+    def set_error_model_random(self, k=7):
+        """model::Error::random(k) — src/model/error.rs:85-90."""
+        self._ck(self.lib.dll.rr_set_error_model(self.h, k, 0, None, None, None, None, None))
+        self.k = k
+
+    def set_error_model(self, k, entries):
+        """entries: list of (key bytes, [(alt bytes, weight), ...]) as loaded by Error::from_stream."""
+        keys = b"".join(e[0] for e in entries)
+        alt_begin = np.zeros(len(entries) + 1, np.uint32)
+        alts, weights = [], []
+        for i, (_key, al) in enumerate(entries):
+            alt_begin[i + 1] = alt_begin[i] + len(al)
+            for a, w in al:
+                alts.append(a)
+                weights.append(w)
+        alt_off = np.zeros(len(alts) + 1, np.uint32)
+        np.cumsum([len(a) for a in alts], out=alt_off[1:]) if alts else None
+        bytes_ = np.frombuffer(b"".join(alts) + b"\0", dtype=np.uint8)
+        w = np.asarray(weights + [0.0], dtype=np.float64)
+        kb = np.frombuffer(keys + b"\0", dtype=np.uint8)
+        self._ck(self.lib.dll.rr_set_error_model(self.h, k, len(entries), kb.ctypes.data, alt_begin.ctypes.data,
+                                                 alt_off.ctypes.data, bytes_.ctypes.data, w.ctypes.data))
+        self.k = k
+
+    def set_qscore_model(self, max_k, entries):
+        """entries: list of (cigar bytes, [score...], [weight...]) as loaded by Quality::from_stream."""
+        cig = b"".join(e[0] for e in entries)
+        cigar_off = np.zeros(len(entries) + 1, np.uint32)
+        score_off = np.zeros(len(entries) + 1, np.uint32)
+        scores, weights = [], []
+        for i, (c, s, w) in enumerate(entries):
+            cigar_off[i + 1] = cigar_off[i] + len(c)
+            score_off[i + 1] = score_off[i] + len(s)
+            scores += list(s)
+            weights += list(w)
+        sc = np.asarray(scores + [0], dtype=np.uint8)
+        w = np.asarray(weights + [0.0], dtype=np.float64)
+        cb = np.frombuffer(cig + b"\0", dtype=np.uint8)
+        self._ck(self.lib.dll.rr_set_qscore_model(self.h, max_k, len(entries), cb.ctypes.data, cigar_off.ctypes.data,
+                                                  score_off.ctypes.data, sc.ctypes.data, w.ctypes.data))
+
+    def set_qscore_model_random(self):
+        """model::Quality::random() — src/model/quality.rs:80-91."""
+        e = [(c, list(range(1, 21)), [1.0] * 20) for c in (b"=", b"X", b"I")]
+        self.set_qscore_model(1, e)
+
+    def set_qscore_model_ideal(self):
+        """model::Quality::ideal() — src/model/quality.rs:94-110."""
+        r = lambda a, b: (list(range(a, b + 1)), [1.0] * (b - a + 1))
+        e = [(b"X",) + r(1, 3), (b"I",) + r(1, 3), (b"=",) + r(4, 7), (b"===",) + r(8, 20), (b"=====",) + r(21, 30),
+             (b"=======",) + r(31, 40), (b"=========",) + r(41, 50)]
+        self.set_qscore_model(9, e)
+
+    def set_adapter(self, start, end, start_rate, start_amount, end_rate, end_amount):
+        self._ck(self.lib.dll.rr_set_adapter(self.h, start, len(start), end, len(end), start_rate, start_amount, end_rate, end_amount))
+
+    def set_glitch(self, rate, size, skip):
+        self._ck(self.lib.dll.rr_set_glitch(self.h, rate, size, skip))
+
+    # -- the hot path ------------------------------------------------------------------------
+    def generate(self, descs):
+        """generate_read over a batch of work items (numpy array of DESC_DTYPE); host in, host out."""
+        descs = np.ascontiguousarray(descs, dtype=DESC_DTYPE)
+        b = rr_batch()
+        self._ck(self.lib.dll.rr_generate(self.h, len(descs), descs.ctypes.data, C.byref(b)))
+        return Batch(b)
+
+    def upload(self, descs):
+        descs = np.ascontiguousarray(descs, dtype=DESC_DTYPE)
+        self._ck(self.lib.dll.rr_upload(self.h, len(descs), descs.ctypes.data))
+
+    def run(self):
+        self._ck(self.lib.dll.rr_run(self.h))
+
+    def download(self):
+        b = rr_batch()
+        self._ck(self.lib.dll.rr_download(self.h, C.byref(b)))
+        return Batch(b)
+
+    def kernel_launches(self):
+        return int(self.lib.dll.rr_kernel_launches(self.h))
+
+    def last_run_ms(self):
+        ms = (C.c_float * 4)()
+        self._ck(self.lib.dll.rr_last_run_ms(self.h, ms))
+        return dict(total=ms[0], read_kernel=ms[1], qscore=ms[2], pack=ms[3])
+
+    def last_run_bases(self):
+        return int(self.lib.dll.rr_last_run_bases(self.h))
+
+    # -- debug / parity hooks ------------------------------------------------------------------
+    def debug_align(self, query, target):
+        out = (C.c_uint8 * (len(query) + len(target) + 1))()
+        n, e = C.c_uint32(), C.c_uint32()
+        self._ck(self.lib.dll.rr_debug_align(self.h, query, len(query), target, len(target), out, C.byref(n), C.byref(e)))
+        return e.value, bytes(out[:n.value]).decode()
+
+    def debug_rng_words(self, seed, first, n):
+        out = np.zeros(n, dtype=np.uint32)
+        self._ck(self.lib.dll.rr_debug_rng_words(self.h, seed, first, n, out.ctypes.data))
+        return out
+
+    def debug_fetch(self, i, which, cap=1 << 22):
+        out = (C.c_uint8 * cap)()
+        n = C.c_uint64()
+        self._ck(self.lib.dll.rr_debug_fetch(self.h, i, {"raw": 0, "cigar": 1}[which], out, cap, C.byref(n)))
+        return bytes(out[:n.value])
+
+
+def descs_from_oracle_items(d12, identity):
+    """Convert the oracle feeder's (n,12) u64 item table into rr_desc records (test helper)."""
+    n = len(d12)
+    out = np.zeros(n, dtype=DESC_DTYPE)
+    out["type"] = d12[:, 0]
+    out["ref_idx"] = d12[:, 1]
+    out["strand"] = d12[:, 2]
+    out["start"] = d12[:, 3]
+    out["end"] = d12[:, 4]
+    out["has_chimera"] = d12[:, 5]
+    out["ctype"] = d12[:, 6]
+    out["cref_idx"] = d12[:, 7]
+    out["cstrand"] = d12[:, 8]
+    out["cstart"] = d12[:, 9]
+    out["cend"] = d12[:, 10]
+    out["seed"] = d12[:, 11]
+    out["identity"] = identity
+    return out

@@ -1,0 +1,703 @@
+// rustyread_b200 — context, device tables, launch plumbing and the C ABI (include/rustyread_b200.h).
+// There is no CPU fallback anywhere in this file: without a usable CUDA device rr_create fails.
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <numeric>
+#include <string>
+#include <vector>
+
+#include "rr_qscore_kernel.cuh"
+#include "rr_read_kernel.cuh"
+
+using namespace rr;
+
+#define RR_API extern "C" __attribute__((visibility("default")))
+
+static std::string g_create_error;
+
+struct DevBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+  bool ensure(size_t bytes) {
+    if (bytes <= cap) return true;
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+    size_t want = bytes + bytes / 8 + 256;
+    if (cudaMalloc(&p, want) != cudaSuccess) { cudaGetLastError(); return false; }
+    cap = want;
+    return true;
+  }
+  void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+  template <class T> T* as() const { return (T*)p; }
+};
+struct PinBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+  bool ensure(size_t bytes) {
+    if (bytes <= cap) return true;
+    if (p) cudaFreeHost(p);
+    p = nullptr;
+    cap = 0;
+    size_t want = bytes + bytes / 8 + 256;
+    if (cudaHostAlloc(&p, want, cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError(); return false; }
+    cap = want;
+    return true;
+  }
+  void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
+  template <class T> T* as() const { return (T*)p; }
+};
+
+struct rr_ctx {
+  int device = 0;
+  int n_sm = 0;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+  std::string err;
+  uint64_t launches = 0;
+  float last_ms[4] = {0, 0, 0, 0};
+  uint64_t last_bases = 0, last_bytes = 0;
+
+  // models
+  DeviceModels M{};
+  QscoreModelDev Q{};
+  bool have_refs = false, have_error = false, have_qscore = false, have_adapter = false, have_glitch = false;
+  std::vector<uint64_t> ref_len;
+  std::vector<uint8_t> ref_circ;
+  double glitch_mean_dist = 0, glitch_mean_size = 0;
+  DevBuf d_ref, d_ref_off, d_ref_circ;
+  DevBuf d_em_index, d_em_alt_begin, d_em_alt_off, d_em_alt_bytes, d_em_cum, d_em_scale;
+  DevBuf d_adapter;
+  DevBuf d_q_tab_off, d_q_tab, d_q_dist_off, d_q_scores, d_q_cum, d_q_scale;
+
+  // batch
+  uint64_t n = 0;
+  std::vector<rr_desc> descs;
+  std::vector<uint64_t> h_raw_off, h_out_off;
+  std::vector<uint32_t> h_order;
+  double slack = 1.5;
+  uint64_t max_raw_cap = 0;
+  DevBuf d_descs, d_order, d_queue, d_raw_off, d_out_off, d_raw, d_err, d_cig;
+  DevBuf d_raw_len, d_err_len, d_cig_len, d_q_cursor, d_real_id, d_status, d_packed_off, d_totals;
+  DevBuf d_seq, d_qual;
+  DevBuf d_sc_rows, d_sc_ops, d_sc_grec, d_sc_gseq;
+  uint64_t sc_rows_cap = 32768, sc_ops_cap = 8192, sc_grec_cap = 0, sc_gseq_cap = 0;
+  uint32_t n_warps = 0, read_grid = 0;
+  bool ran = false;
+
+  PinBuf h_seq, h_qual, h_off, h_len, h_id, h_totals, h_status;
+};
+
+static int fail(rr_ctx* c, int code, const std::string& msg) {
+  if (c) c->err = msg; else g_create_error = msg;
+  return code;
+}
+#define CK(call)                                                                               \
+  do {                                                                                         \
+    cudaError_t e_ = (call);                                                                   \
+    if (e_ != cudaSuccess) {                                                                   \
+      cudaGetLastError();                                                                      \
+      return fail(ctx, RR_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_));       \
+    }                                                                                          \
+  } while (0)
+#define ENSURE(buf, bytes) \
+  do { if (!(buf).ensure(bytes)) return fail(ctx, RR_ERR_CUDA, "out of memory allocating " #buf); } while (0)
+
+template <class T>
+static bool upload(rr_ctx* ctx, DevBuf& b, const std::vector<T>& v) {
+  size_t bytes = std::max<size_t>(1, v.size()) * sizeof(T);
+  if (!b.ensure(bytes)) return false;
+  if (!v.empty() && cudaMemcpyAsync(b.p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess) return false;
+  return cudaStreamSynchronize(ctx->stream) == cudaSuccess;
+}
+
+RR_API int rr_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+  return n;
+}
+
+RR_API int rr_create(int device, rr_ctx** out) {
+  rr_ctx* ctx = nullptr;
+  if (!out) return fail(nullptr, RR_ERR_ARG, "rr_create: out is NULL");
+  *out = nullptr;
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n == 0) {
+    cudaGetLastError();
+    return fail(nullptr, RR_ERR_CUDA, "rr_create: no CUDA device available (this library has no CPU fallback)");
+  }
+  if (device < 0 || device >= n) return fail(nullptr, RR_ERR_ARG, "rr_create: device index out of range");
+  CK(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  CK(cudaGetDeviceProperties(&prop, device));
+  if (prop.major < 10) return fail(nullptr, RR_ERR_CUDA, "rr_create: kernels are built for sm_100a only");
+  ctx = new rr_ctx();
+  ctx->device = device;
+  ctx->n_sm = prop.multiProcessorCount;
+  if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return fail(nullptr, RR_ERR_CUDA, "cudaStreamCreate failed"); }
+  for (auto& ev : ctx->ev) cudaEventCreate(&ev);
+  *out = ctx;
+  return RR_OK;
+}
+
+RR_API void rr_destroy(rr_ctx* ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  DevBuf* bufs[] = {&ctx->d_ref, &ctx->d_ref_off, &ctx->d_ref_circ, &ctx->d_em_index, &ctx->d_em_alt_begin, &ctx->d_em_alt_off,
+                    &ctx->d_em_alt_bytes, &ctx->d_em_cum, &ctx->d_em_scale, &ctx->d_adapter, &ctx->d_q_tab_off, &ctx->d_q_tab,
+                    &ctx->d_q_dist_off, &ctx->d_q_scores, &ctx->d_q_cum, &ctx->d_q_scale, &ctx->d_descs, &ctx->d_order, &ctx->d_queue,
+                    &ctx->d_raw_off, &ctx->d_out_off, &ctx->d_raw, &ctx->d_err, &ctx->d_cig, &ctx->d_raw_len, &ctx->d_err_len,
+                    &ctx->d_cig_len, &ctx->d_q_cursor, &ctx->d_real_id, &ctx->d_status, &ctx->d_packed_off, &ctx->d_totals,
+                    &ctx->d_seq, &ctx->d_qual, &ctx->d_sc_rows, &ctx->d_sc_ops, &ctx->d_sc_grec, &ctx->d_sc_gseq};
+  for (auto* b : bufs) b->release();
+  PinBuf* pins[] = {&ctx->h_seq, &ctx->h_qual, &ctx->h_off, &ctx->h_len, &ctx->h_id, &ctx->h_totals, &ctx->h_status};
+  for (auto* b : pins) b->release();
+  for (auto& ev : ctx->ev) if (ev) cudaEventDestroy(ev);
+  if (ctx->stream) cudaStreamDestroy(ctx->stream);
+  delete ctx;
+}
+
+RR_API const char* rr_last_error(const rr_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+RR_API uint64_t rr_kernel_launches(const rr_ctx* ctx) { return ctx ? ctx->launches : 0; }
+RR_API uint64_t rr_last_run_bases(const rr_ctx* ctx) { return ctx ? ctx->last_bases : 0; }
+RR_API void* rr_stream(const rr_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
+RR_API int rr_last_run_ms(const rr_ctx* ctx, float* ms4) {
+  if (!ctx || !ms4) return RR_ERR_ARG;
+  for (int i = 0; i < 4; ++i) ms4[i] = ctx->last_ms[i];
+  return RR_OK;
+}
+
+// ---- references -------------------------------------------------------------------------------------
+RR_API int rr_set_references(rr_ctx* ctx, uint64_t n, const uint8_t* const* seq, const uint64_t* len, const uint8_t* circular) {
+  if (!ctx) return RR_ERR_ARG;
+  if (n == 0 || !seq || !len) return fail(ctx, RR_ERR_ARG, "rr_set_references: no contigs");
+  if (n > 0xffffffffULL) return fail(ctx, RR_ERR_UNSUPPORTED, "rr_set_references: too many contigs");
+  CK(cudaSetDevice(ctx->device));
+  std::vector<uint64_t> off(n + 1, 0);
+  for (uint64_t i = 0; i < n; ++i) off[i + 1] = off[i] + len[i];
+  ENSURE(ctx->d_ref, std::max<uint64_t>(16, off[n]));
+  for (uint64_t i = 0; i < n; ++i)
+    if (len[i]) CK(cudaMemcpyAsync(ctx->d_ref.as<uint8_t>() + off[i], seq[i], len[i], cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  ctx->ref_len.assign(len, len + n);
+  ctx->ref_circ.assign(n, 0);
+  if (circular) for (uint64_t i = 0; i < n; ++i) ctx->ref_circ[i] = circular[i] ? 1 : 0;
+  if (!upload(ctx, ctx->d_ref_off, off) || !upload(ctx, ctx->d_ref_circ, ctx->ref_circ)) return fail(ctx, RR_ERR_CUDA, "rr_set_references: upload failed");
+  ctx->M.ref_bytes = ctx->d_ref.as<uint8_t>();
+  ctx->M.ref_off = ctx->d_ref_off.as<uint64_t>();
+  ctx->M.ref_circ = ctx->d_ref_circ.as<uint8_t>();
+  ctx->M.n_refs = (uint32_t)n;
+  ctx->have_refs = true;
+  return RR_OK;
+}
+
+// ---- error model ---------------------------------------------------------------------------------------
+RR_API int rr_set_error_model(rr_ctx* ctx, uint32_t k, uint64_t n_keys, const uint8_t* keys, const uint32_t* alt_begin,
+                              const uint32_t* alt_off, const uint8_t* alt_bytes, const double* weights) {
+  if (!ctx) return RR_ERR_ARG;
+  if (k == 0 || k > 31) return fail(ctx, RR_ERR_UNSUPPORTED, "rr_set_error_model: k must be in 1..31");
+  CK(cudaSetDevice(ctx->device));
+  ctx->M.k = k;
+  if (n_keys == 0) {  // Error::random(k)
+    ctx->M.em_index = nullptr;
+    ctx->have_error = true;
+    return RR_OK;
+  }
+  if (!keys || !alt_begin || !alt_off || !alt_bytes || !weights) return fail(ctx, RR_ERR_ARG, "rr_set_error_model: NULL table");
+  if (k > 12) return fail(ctx, RR_ERR_UNSUPPORTED, "rr_set_error_model: file models need k <= 12 (dense 4^k index)");
+  const uint64_t n_codes = 1ULL << (2 * k);
+  std::vector<int32_t> index(n_codes, -1);
+  const uint32_t n_alts = alt_begin[n_keys];
+  std::vector<double> cum(n_alts), scale(n_keys);
+  for (uint64_t i = 0; i < n_keys; ++i) {
+    uint32_t code = 0;
+    for (uint32_t x = 0; x < k; ++x) {
+      uint8_t c = keys[i * k + x];
+      uint32_t s = c == 'A' ? 0 : c == 'C' ? 1 : c == 'G' ? 2 : c == 'T' ? 3 : 4;
+      if (s > 3) return fail(ctx, RR_ERR_UNSUPPORTED, "rr_set_error_model: key with a byte outside ACGT");
+      code |= s << (2 * (k - 1 - x));
+    }
+    index[code] = (int32_t)i;  // later duplicates replace earlier ones, like HashMap::insert
+    uint32_t a0 = alt_begin[i], a1 = alt_begin[i + 1];
+    if (a1 <= a0) return fail(ctx, RR_ERR_ARG, "rr_set_error_model: key without alternatives (the reference panics when it is sampled)");
+    if (!weighted_index_build(weights + a0, a1 - a0, cum.data() + a0, &scale[i]))
+      return fail(ctx, RR_ERR_ARG, "rr_set_error_model: invalid weights (WeightedIndex::new fails in the reference)");
+    for (uint32_t j = a0; j < a1; ++j)
+      if (alt_off[j + 1] - alt_off[j] > (uint32_t)ALT_MAX) return fail(ctx, RR_ERR_UNSUPPORTED, "rr_set_error_model: alternative longer than 64 bytes");
+  }
+  std::vector<uint32_t> ab(alt_begin, alt_begin + n_keys + 1), ao(alt_off, alt_off + n_alts + 1);
+  std::vector<uint8_t> bytes(alt_bytes, alt_bytes + alt_off[n_alts]);
+  if (!upload(ctx, ctx->d_em_index, index) || !upload(ctx, ctx->d_em_alt_begin, ab) || !upload(ctx, ctx->d_em_alt_off, ao) ||
+      !upload(ctx, ctx->d_em_alt_bytes, bytes) || !upload(ctx, ctx->d_em_cum, cum) || !upload(ctx, ctx->d_em_scale, scale))
+    return fail(ctx, RR_ERR_CUDA, "rr_set_error_model: upload failed");
+  ctx->M.em_index = ctx->d_em_index.as<int32_t>();
+  ctx->M.em_alt_begin = ctx->d_em_alt_begin.as<uint32_t>();
+  ctx->M.em_alt_off = ctx->d_em_alt_off.as<uint32_t>();
+  ctx->M.em_alt_bytes = ctx->d_em_alt_bytes.as<uint8_t>();
+  ctx->M.em_cum = ctx->d_em_cum.as<double>();
+  ctx->M.em_scale = ctx->d_em_scale.as<double>();
+  ctx->have_error = true;
+  return RR_OK;
+}
+
+// ---- qscore model ------------------------------------------------------------------------------------------
+RR_API int rr_set_qscore_model(rr_ctx* ctx, uint32_t max_k, uint64_t n, const uint8_t* cigars, const uint32_t* cigar_off,
+                               const uint32_t* score_off, const uint8_t* scores, const double* weights) {
+  if (!ctx) return RR_ERR_ARG;
+  if (n == 0 || !cigars || !cigar_off || !score_off || !scores || !weights) return fail(ctx, RR_ERR_ARG, "rr_set_qscore_model: NULL table");
+  if (max_k == 0) return fail(ctx, RR_ERR_ARG, "rr_set_qscore_model: max_k == 0");
+  if (max_k > 12) return fail(ctx, RR_ERR_UNSUPPORTED, "rr_set_qscore_model: max_k > 12 (dense 4^l window tables)");
+  if (n > 65000) return fail(ctx, RR_ERR_UNSUPPORTED, "rr_set_qscore_model: more than 65000 entries");
+  CK(cudaSetDevice(ctx->device));
+  std::map<std::string, uint32_t> key2dist;
+  for (uint64_t i = 0; i < n; ++i) key2dist[std::string((const char*)cigars + cigar_off[i], cigar_off[i + 1] - cigar_off[i])] = (uint32_t)i;
+  if (!key2dist.count("=") || !key2dist.count("X") || !key2dist.count("I"))
+    return fail(ctx, RR_ERR_ARG, "rr_set_qscore_model: model must contain '=', 'X' and 'I' (QualityNotMinimalCigarString)");
+  std::vector<uint32_t> dist_off(score_off, score_off + n + 1);
+  const uint32_t n_sc = score_off[n];
+  std::vector<double> cum(std::max<uint32_t>(1, n_sc)), scale(n);
+  std::vector<char> dist_ok(n, 1);
+  for (uint64_t i = 0; i < n; ++i) {
+    uint32_t a0 = score_off[i], a1 = score_off[i + 1];
+    if (a1 <= a0 || !weighted_index_build(weights + a0, a1 - a0, cum.data() + a0, &scale[i])) dist_ok[i] = 0;
+  }
+  const uint32_t margin = (max_k - 1) / 2;
+  std::vector<uint32_t> tab_off(2 * margin + 2, 0);
+  std::vector<uint16_t> tab;
+  static const char SYM[4] = {'=', 'X', 'I', 'D'};
+  for (uint32_t l = 1; l <= 2 * margin + 1; l += 2) {
+    tab_off[l] = (uint32_t)tab.size();
+    const uint64_t cnt = 1ULL << (2 * l);
+    std::string w(l, '=');
+    for (uint64_t code = 0; code < cnt; ++code) {
+      for (uint32_t y = 0; y < l; ++y) w[y] = SYM[(code >> (2 * y)) & 3];
+      // get_qscore: strip one char from both ends until the window is known (quality.rs:118-130)
+      uint16_t id = 0xFFFF;
+      size_t b = 0, len = l;
+      for (;;) {
+        auto it = key2dist.find(w.substr(b, len));
+        if (it != key2dist.end()) { id = (uint16_t)it->second; break; }
+        if (len <= 2) break;
+        b += 1;
+        len -= 2;
+      }
+      if (id != 0xFFFF && !dist_ok[id]) {
+        // WeightedIndex::new(..).unwrap() would panic when this entry is sampled; only fatal if reachable
+        if (w[l / 2] != 'D') return fail(ctx, RR_ERR_ARG, "rr_set_qscore_model: entry '" + w.substr(b, len) + "' has invalid weights");
+        id = 0xFFFF;
+      }
+      tab.push_back(id);
+    }
+  }
+  std::vector<uint8_t> sc(scores, scores + n_sc);
+  if (!upload(ctx, ctx->d_q_tab_off, tab_off) || !upload(ctx, ctx->d_q_tab, tab) || !upload(ctx, ctx->d_q_dist_off, dist_off) ||
+      !upload(ctx, ctx->d_q_scores, sc) || !upload(ctx, ctx->d_q_cum, cum) || !upload(ctx, ctx->d_q_scale, scale))
+    return fail(ctx, RR_ERR_CUDA, "rr_set_qscore_model: upload failed");
+  ctx->Q.max_k = max_k;
+  ctx->Q.tab_off = ctx->d_q_tab_off.as<uint32_t>();
+  ctx->Q.tab = ctx->d_q_tab.as<uint16_t>();
+  ctx->Q.dist_off = ctx->d_q_dist_off.as<uint32_t>();
+  ctx->Q.scores = ctx->d_q_scores.as<uint8_t>();
+  ctx->Q.cum = ctx->d_q_cum.as<double>();
+  ctx->Q.scale = ctx->d_q_scale.as<double>();
+  ctx->have_qscore = true;
+  return RR_OK;
+}
+
+// ---- adapter / glitch -----------------------------------------------------------------------------------------
+RR_API int rr_set_adapter(rr_ctx* ctx, const uint8_t* start, uint64_t start_len, const uint8_t* end, uint64_t end_len,
+                          double start_rate, double start_amount, double end_rate, double end_amount) {
+  if (!ctx) return RR_ERR_ARG;
+  CK(cudaSetDevice(ctx->device));
+  // Adapter::new, src/model/adapter.rs:23-61 (including the double division by 100 at :34-38)
+  DeviceModels& M = ctx->M;
+  M.has_start = M.has_end = 0;
+  if (!(start_len == 0 || start_rate == 0.0 || start_amount == 0.0)) {
+    double a = start_amount / 100.0;
+    if (!beta_new(2.0 * a, 2.0 - 2.0 * (a / 100.0), M.start_beta)) return fail(ctx, RR_ERR_ARG, "rr_set_adapter: invalid start Beta parameters");
+    M.has_start = 1;
+  }
+  if (!(end_len == 0 || end_rate == 0.0 || end_amount == 0.0)) {
+    double a = end_amount / 100.0;
+    if (!beta_new(2.0 * a, 2.0 - 2.0 * a, M.end_beta)) return fail(ctx, RR_ERR_ARG, "rr_set_adapter: invalid end Beta parameters");
+    M.has_end = 1;
+  }
+  M.start_rate = start_rate / 100.0;
+  M.end_rate = end_rate / 100.0;
+  // gen_bool panics outside [0,1] (rand Bernoulli::new)
+  if (!(M.start_rate >= 0.0 && M.start_rate <= 1.0) || !(M.end_rate >= 0.0 && M.end_rate <= 1.0))
+    return fail(ctx, RR_ERR_ARG, "rr_set_adapter: rate outside 0..100 (gen_bool panics in the reference)");
+  std::vector<uint8_t> bytes;
+  if (start_len) bytes.insert(bytes.end(), start, start + start_len);
+  if (end_len) bytes.insert(bytes.end(), end, end + end_len);
+  if (!upload(ctx, ctx->d_adapter, bytes)) return fail(ctx, RR_ERR_CUDA, "rr_set_adapter: upload failed");
+  M.adapter_bytes = ctx->d_adapter.as<uint8_t>();
+  M.start_len = (uint32_t)start_len;
+  M.end_len = (uint32_t)end_len;
+  ctx->have_adapter = true;
+  return RR_OK;
+}
+
+RR_API int rr_set_glitch(rr_ctx* ctx, double rate, double size, double skip) {
+  if (!ctx) return RR_ERR_ARG;
+  DeviceModels& M = ctx->M;
+  // Glitch::new, src/model/glitch.rs:20-48
+  M.has_distance = 0;
+  if (rate != 0.0) {
+    if (!geometric_new(rate > 1.0 ? 1.0 / rate : 1.0, M.g_dist)) return fail(ctx, RR_ERR_ARG, "rr_set_glitch: invalid rate");
+    M.has_distance = 1;
+  }
+  if (!geometric_new(size > 1.0 ? 1.0 / size : 1.0, M.g_size)) return fail(ctx, RR_ERR_ARG, "rr_set_glitch: invalid size");
+  if (!geometric_new(skip > 1.0 ? 1.0 / skip : 1.0, M.g_skip)) return fail(ctx, RR_ERR_ARG, "rr_set_glitch: invalid skip");
+  ctx->glitch_mean_dist = M.has_distance ? (1.0 - M.g_dist.p) / M.g_dist.p : 0.0;
+  ctx->glitch_mean_size = (1.0 - M.g_size.p) / M.g_size.p;
+  ctx->have_glitch = true;
+  return RR_OK;
+}
+
+// ---- batch planning ------------------------------------------------------------------------------------------
+static inline uint64_t align16(uint64_t x) { return (x + 15) & ~15ULL; }
+
+static int frag_len(rr_ctx* ctx, uint32_t type, uint32_t ref_idx, uint64_t start, uint64_t end, uint64_t& out) {
+  if (type == RR_JUNK || type == RR_RANDOM) { out = end; return RR_OK; }
+  if (type != RR_REAL) return fail(ctx, RR_ERR_ARG, "rr_upload: unknown read type");
+  if (ref_idx >= ctx->ref_len.size()) return fail(ctx, RR_ERR_ARG, "rr_upload: ref_idx out of range");
+  uint64_t rl = ctx->ref_len[ref_idx];
+  if (start < end) {
+    if (end > rl) return fail(ctx, RR_ERR_ARG, "rr_upload: fragment end beyond the contig (the reference panics)");
+    out = end - start;
+  } else if (ctx->ref_circ[ref_idx]) {
+    if (start > rl || end > rl) return fail(ctx, RR_ERR_ARG, "rr_upload: fragment beyond the contig (the reference panics)");
+    out = rl - start + end;
+  } else out = 0;
+  return RR_OK;
+}
+
+static int plan(rr_ctx* ctx) {
+  const uint64_t n = ctx->n;
+  const DeviceModels& M = ctx->M;
+  const uint64_t adapters = (uint64_t)M.start_len + M.end_len;
+  ctx->h_raw_off.assign(n + 1, 0);
+  ctx->h_out_off.assign(n + 1, 0);
+  ctx->h_order.resize(n);
+  ctx->max_raw_cap = 0;
+  std::vector<uint64_t> raw_cap(n);
+  double max_ng = 0;
+  for (uint64_t i = 0; i < n; ++i) {
+    const rr_desc& d = ctx->descs[i];
+    uint64_t f1 = 0, f2 = 0;
+    int rc = frag_len(ctx, d.type, d.ref_idx, d.start, d.end, f1);
+    if (rc) return rc;
+    if (d.has_chimera && (rc = frag_len(ctx, d.ctype, d.cref_idx, d.cstart, d.cend, f2))) return rc;
+    if (!(d.identity <= 1.0 && d.identity >= -1.0)) return fail(ctx, RR_ERR_ARG, "rr_upload: identity outside [0,1]");
+    uint64_t rcap = 2ULL * M.k + f1 + f2 + 2 * adapters;
+    raw_cap[i] = rcap;
+    ctx->max_raw_cap = std::max(ctx->max_raw_cap, rcap);
+    double target = std::max(0.0, (1.0 - d.identity)) * (double)rcap;
+    double ng = 0, gl = 0;
+    if (M.has_distance) {
+      ng = (double)rcap / (ctx->glitch_mean_dist + 1.0);
+      ng = (ng + 6.0 * std::sqrt(ng) + 30.0) * ctx->slack;
+      gl = ng * (ctx->glitch_mean_size + 1.0);
+      max_ng = std::max(max_ng, ng);
+    }
+    uint64_t ocap = align16(rcap + (uint64_t)std::ceil(target) + (uint64_t)gl + (uint64_t)(64 * ctx->slack) + ALT_MAX + 16);
+    ctx->h_raw_off[i + 1] = ctx->h_raw_off[i] + align16(rcap + 16);
+    ctx->h_out_off[i + 1] = ctx->h_out_off[i] + ocap;
+  }
+  std::iota(ctx->h_order.begin(), ctx->h_order.end(), 0u);
+  std::stable_sort(ctx->h_order.begin(), ctx->h_order.end(), [&](uint32_t a, uint32_t b) { return raw_cap[a] > raw_cap[b]; });
+  ctx->sc_grec_cap = (uint64_t)max_ng + 8;
+  ctx->sc_gseq_cap = align16((uint64_t)(max_ng * (ctx->glitch_mean_size + 1.0)) + 64);
+  return RR_OK;
+}
+
+static int upload_plan(rr_ctx* ctx) {
+  const uint64_t n = ctx->n;
+  if (!upload(ctx, ctx->d_raw_off, ctx->h_raw_off) || !upload(ctx, ctx->d_out_off, ctx->h_out_off) || !upload(ctx, ctx->d_order, ctx->h_order))
+    return fail(ctx, RR_ERR_CUDA, "rr_upload: H2D of the plan failed");
+  ENSURE(ctx->d_raw, ctx->h_raw_off[n] + 16);
+  ENSURE(ctx->d_err, ctx->h_out_off[n] + 16);
+  ENSURE(ctx->d_cig, ctx->h_out_off[n] + 16);
+  // persistent grid: 4 blocks of 8 warps per SM, fewer if the batch is small
+  uint32_t want_blocks = (uint32_t)std::min<uint64_t>((uint64_t)ctx->n_sm * 4, (n + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK);
+  ctx->read_grid = std::max<uint32_t>(1, want_blocks);
+  ctx->n_warps = ctx->read_grid * WARPS_PER_BLOCK;
+  ENSURE(ctx->d_sc_rows, (uint64_t)ctx->n_warps * ctx->sc_rows_cap * 8);
+  ENSURE(ctx->d_sc_ops, (uint64_t)ctx->n_warps * ctx->sc_ops_cap);
+  ENSURE(ctx->d_sc_grec, (uint64_t)ctx->n_warps * ctx->sc_grec_cap * sizeof(GlitchRec));
+  ENSURE(ctx->d_sc_gseq, (uint64_t)ctx->n_warps * ctx->sc_gseq_cap);
+  return RR_OK;
+}
+
+RR_API int rr_upload(rr_ctx* ctx, uint64_t n, const rr_desc* descs) {
+  if (!ctx) return RR_ERR_ARG;
+  if (!(ctx->have_refs && ctx->have_error && ctx->have_qscore && ctx->have_adapter && ctx->have_glitch))
+    return fail(ctx, RR_ERR_ARG, "rr_upload: references and all four models must be set first");
+  if (n == 0 || !descs) return fail(ctx, RR_ERR_ARG, "rr_upload: empty batch");
+  if (n > 0x7fffffffULL) return fail(ctx, RR_ERR_UNSUPPORTED, "rr_upload: more than 2^31 reads in one batch");
+  CK(cudaSetDevice(ctx->device));
+  ctx->ran = false;
+  ctx->n = n;
+  ctx->descs.assign(descs, descs + n);
+  ctx->slack = 1.5;
+  int rc = plan(ctx);
+  if (rc) return rc;
+  ENSURE(ctx->d_descs, n * sizeof(rr_desc));
+  CK(cudaMemcpyAsync(ctx->d_descs.p, descs, n * sizeof(rr_desc), cudaMemcpyHostToDevice, ctx->stream));
+  rc = upload_plan(ctx);
+  if (rc) return rc;
+  ENSURE(ctx->d_queue, 16);
+  ENSURE(ctx->d_raw_len, n * 8);
+  ENSURE(ctx->d_err_len, n * 8);
+  ENSURE(ctx->d_cig_len, n * 8);
+  ENSURE(ctx->d_q_cursor, n * 8);
+  ENSURE(ctx->d_real_id, n * 8);
+  ENSURE(ctx->d_status, n * 4);
+  ENSURE(ctx->d_packed_off, (n + 1) * 8);
+  ENSURE(ctx->d_totals, 32);
+  ENSURE(ctx->h_totals, 32);
+  CK(cudaStreamSynchronize(ctx->stream));
+  return RR_OK;
+}
+
+static int launch_all(rr_ctx* ctx) {
+  const uint32_t n = (uint32_t)ctx->n;
+  ReadKernelParams P{};
+  P.M = ctx->M;
+  P.descs = ctx->d_descs.as<rr_desc>();
+  P.order = ctx->d_order.as<uint32_t>();
+  P.n_reads = n;
+  P.queue = ctx->d_queue.as<uint32_t>();
+  P.raw_off = ctx->d_raw_off.as<uint64_t>();
+  P.out_off = ctx->d_out_off.as<uint64_t>();
+  P.raw = ctx->d_raw.as<uint8_t>();
+  P.err = ctx->d_err.as<uint8_t>();
+  P.cig = ctx->d_cig.as<uint8_t>();
+  P.raw_len = ctx->d_raw_len.as<uint64_t>();
+  P.err_len = ctx->d_err_len.as<uint64_t>();
+  P.cig_len = ctx->d_cig_len.as<uint64_t>();
+  P.q_cursor = ctx->d_q_cursor.as<uint64_t>();
+  P.real_id = ctx->d_real_id.as<double>();
+  P.status = ctx->d_status.as<uint32_t>();
+  P.sc_rows = ctx->d_sc_rows.as<uint64_t>();  P.sc_rows_cap = ctx->sc_rows_cap;
+  P.sc_ops = ctx->d_sc_ops.as<uint8_t>();     P.sc_ops_cap = ctx->sc_ops_cap;
+  P.sc_grec = ctx->d_sc_grec.as<GlitchRec>(); P.sc_grec_cap = ctx->sc_grec_cap;
+  P.sc_gseq = ctx->d_sc_gseq.as<uint8_t>();   P.sc_gseq_cap = ctx->sc_gseq_cap;
+
+  CK(cudaMemsetAsync(ctx->d_queue.p, 0, 16, ctx->stream));
+  CK(cudaEventRecord(ctx->ev[0], ctx->stream));
+  rr_read_kernel<<<ctx->read_grid, WARPS_PER_BLOCK * 32, 0, ctx->stream>>>(P);
+  CK(cudaGetLastError());
+  CK(cudaEventRecord(ctx->ev[1], ctx->stream));
+  rr_scan_kernel<<<1, 1024, 0, ctx->stream>>>(ctx->d_err_len.as<uint64_t>(), ctx->d_status.as<uint32_t>(), n, ctx->M.k,
+                                              ctx->d_packed_off.as<uint64_t>(), ctx->d_totals.as<uint64_t>());
+  CK(cudaGetLastError());
+  CK(cudaMemcpyAsync(ctx->h_totals.p, ctx->d_totals.p, 24, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));  // the packed size decides the output allocation
+  const uint64_t total = ctx->h_totals.as<uint64_t>()[0];
+  ENSURE(ctx->d_seq, total + 16);
+  ENSURE(ctx->d_qual, total + 16);
+
+  QscoreKernelParams QP{};
+  QP.Q = ctx->Q;
+  QP.descs = P.descs;
+  QP.order = P.order;
+  QP.n_reads = n;
+  QP.queue = ctx->d_queue.as<uint32_t>() + 1;
+  QP.out_off = P.out_off;
+  QP.cig = P.cig;
+  QP.cig_len = P.cig_len;
+  QP.err_len = P.err_len;
+  QP.q_cursor = P.q_cursor;
+  QP.packed_off = ctx->d_packed_off.as<uint64_t>();
+  QP.qual = ctx->d_qual.as<uint8_t>();
+  QP.status = P.status;
+  uint32_t qgrid = (uint32_t)std::min<uint64_t>((uint64_t)ctx->n_sm * 8, n);
+  rr_qscore_kernel<<<qgrid, Q_THREADS, 0, ctx->stream>>>(QP);
+  CK(cudaGetLastError());
+  CK(cudaEventRecord(ctx->ev[2], ctx->stream));
+  PackKernelParams K{};
+  K.n_reads = n;
+  K.out_off = P.out_off;
+  K.packed_off = QP.packed_off;
+  K.err_len = P.err_len;
+  K.err = P.err;
+  K.seq = ctx->d_seq.as<uint8_t>();
+  uint32_t pgrid = (uint32_t)std::min<uint64_t>((uint64_t)ctx->n_sm * 8, n);
+  rr_pack_kernel<<<pgrid, 256, 0, ctx->stream>>>(K);
+  CK(cudaGetLastError());
+  CK(cudaEventRecord(ctx->ev[3], ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  ctx->launches += 4;
+  float a = 0, b = 0, c = 0, w = 0;
+  cudaEventElapsedTime(&w, ctx->ev[0], ctx->ev[3]);
+  cudaEventElapsedTime(&a, ctx->ev[0], ctx->ev[1]);
+  cudaEventElapsedTime(&b, ctx->ev[1], ctx->ev[2]);
+  cudaEventElapsedTime(&c, ctx->ev[2], ctx->ev[3]);
+  ctx->last_ms[0] = w; ctx->last_ms[1] = a; ctx->last_ms[2] = b; ctx->last_ms[3] = c;
+  ctx->last_bytes = total;
+  ctx->last_bases = ctx->h_totals.as<uint64_t>()[1];
+  return RR_OK;
+}
+
+RR_API int rr_run(rr_ctx* ctx) {
+  if (!ctx) return RR_ERR_ARG;
+  if (ctx->n == 0) return fail(ctx, RR_ERR_ARG, "rr_run: nothing uploaded");
+  CK(cudaSetDevice(ctx->device));
+  for (int attempt = 0; attempt < 6; ++attempt) {
+    int rc = launch_all(ctx);
+    if (rc) return rc;
+    // status of the qscore kernel may have changed after the scan: re-read the failure count cheaply
+    const uint64_t failed_scan = ctx->h_totals.as<uint64_t>()[2];
+    ENSURE(ctx->h_status, ctx->n * 4);
+    bool need_status = failed_scan != 0;
+    if (!need_status) {
+      // qscore failures are rare and fatal; detect them with one reduction-free pass over the status words
+      CK(cudaMemcpyAsync(ctx->h_status.p, ctx->d_status.p, ctx->n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+      CK(cudaStreamSynchronize(ctx->stream));
+    } else {
+      CK(cudaMemcpyAsync(ctx->h_status.p, ctx->d_status.p, ctx->n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+      CK(cudaStreamSynchronize(ctx->stream));
+    }
+    const uint32_t* st = ctx->h_status.as<uint32_t>();
+    uint64_t grow = 0;
+    for (uint64_t i = 0; i < ctx->n; ++i) {
+      if (st[i] == ST_OK) continue;
+      if (st[i] == ST_OUT_OVERFLOW || st[i] == ST_GLITCH_OVERFLOW) { ++grow; continue; }
+      char buf[256];
+      const char* what = st[i] == ST_ALIGN_TOO_LARGE ? "alignment window beyond the bit-vector scratch (2048 columns)"
+                         : st[i] == ST_REF_PANIC     ? "slice out of range in Change::merge/update_align (the reference panics here)"
+                                                     : "qscore window not in the model (reference: QualityNotMinimalCigarString)";
+      std::snprintf(buf, sizeof buf, "read %llu (seed %llu): %s", (unsigned long long)i, (unsigned long long)ctx->descs[i].seed, what);
+      return fail(ctx, RR_ERR_READ, buf);
+    }
+    if (grow == 0) { ctx->ran = true; return RR_OK; }
+    ctx->slack *= 2.0;  // capacity estimate too small for `grow` reads: re-plan with more slack
+    rc = plan(ctx);
+    if (rc) return rc;
+    rc = upload_plan(ctx);
+    if (rc) return rc;
+  }
+  return fail(ctx, RR_ERR_READ, "rr_run: output capacity still too small after 6 attempts");
+}
+
+RR_API int rr_download(rr_ctx* ctx, rr_batch* out) {
+  if (!ctx || !out) return RR_ERR_ARG;
+  if (!ctx->ran) return fail(ctx, RR_ERR_ARG, "rr_download: no completed rr_run");
+  CK(cudaSetDevice(ctx->device));
+  const uint64_t n = ctx->n, total = ctx->last_bytes;
+  ENSURE(ctx->h_off, (n + 1) * 8);
+  ENSURE(ctx->h_len, n * 8);
+  ENSURE(ctx->h_id, n * 8);
+  ENSURE(ctx->h_seq, total + 16);
+  ENSURE(ctx->h_qual, total + 16);
+  CK(cudaMemcpyAsync(ctx->h_off.p, ctx->d_packed_off.p, (n + 1) * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaMemcpyAsync(ctx->h_len.p, ctx->d_err_len.p, n * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaMemcpyAsync(ctx->h_id.p, ctx->d_real_id.p, n * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  if (total) {
+    CK(cudaMemcpyAsync(ctx->h_seq.p, ctx->d_seq.p, total, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->h_qual.p, ctx->d_qual.p, total, cudaMemcpyDeviceToHost, ctx->stream));
+  }
+  CK(cudaStreamSynchronize(ctx->stream));
+  out->n_reads = n;
+  out->offsets = ctx->h_off.as<uint64_t>();
+  out->lengths = ctx->h_len.as<uint64_t>();
+  out->seq = ctx->h_seq.as<uint8_t>();
+  out->qual = ctx->h_qual.as<uint8_t>();
+  out->real_identity = ctx->h_id.as<double>();
+  out->total_bytes = total;
+  out->total_bases = ctx->last_bases;
+  out->k = ctx->M.k;
+  return RR_OK;
+}
+
+RR_API int rr_generate(rr_ctx* ctx, uint64_t n, const rr_desc* descs, rr_batch* out) {
+  int rc = rr_upload(ctx, n, descs);
+  if (rc) return rc;
+  rc = rr_run(ctx);
+  if (rc) return rc;
+  return rr_download(ctx, out);
+}
+
+// ---- debug / parity hooks ---------------------------------------------------------------------------------------
+__global__ void rr_debug_align_kernel(ReadKernelParams P, const uint8_t* q, uint32_t m, const uint8_t* t, uint32_t n, uint8_t* cigar,
+                                      uint32_t* out) {
+  __shared__ WarpSmem ws;
+  AlignOut a = warp_align(&ws, P, 0, q, m, t, n, cigar, (uint64_t)m + n, threadIdx.x & 31);
+  if (threadIdx.x == 0) { out[0] = a.n_ops; out[1] = a.edits; out[2] = (uint32_t)a.status; }
+}
+
+RR_API int rr_debug_align(rr_ctx* ctx, const uint8_t* query, uint32_t m, const uint8_t* target, uint32_t n, uint8_t* cigar,
+                          uint32_t* cigar_len, uint32_t* edits) {
+  if (!ctx) return RR_ERR_ARG;
+  CK(cudaSetDevice(ctx->device));
+  DevBuf dq, dt, dc, dout;
+  ENSURE(dq, m + 16); ENSURE(dt, n + 16); ENSURE(dc, (size_t)m + n + 16); ENSURE(dout, 16);
+  ENSURE(ctx->d_sc_rows, ctx->sc_rows_cap * 8);
+  ENSURE(ctx->d_sc_ops, ctx->sc_ops_cap);
+  if (m) CK(cudaMemcpyAsync(dq.p, query, m, cudaMemcpyHostToDevice, ctx->stream));
+  if (n) CK(cudaMemcpyAsync(dt.p, target, n, cudaMemcpyHostToDevice, ctx->stream));
+  ReadKernelParams P{};
+  P.sc_rows = ctx->d_sc_rows.as<uint64_t>(); P.sc_rows_cap = ctx->sc_rows_cap;
+  P.sc_ops = ctx->d_sc_ops.as<uint8_t>();    P.sc_ops_cap = ctx->sc_ops_cap;
+  rr_debug_align_kernel<<<1, 32, 0, ctx->stream>>>(P, dq.as<uint8_t>(), m, dt.as<uint8_t>(), n, dc.as<uint8_t>(), dout.as<uint32_t>());
+  CK(cudaGetLastError());
+  ctx->launches += 1;
+  uint32_t res[3];
+  CK(cudaMemcpyAsync(res, dout.p, 12, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  int rc = RR_OK;
+  if (res[2] != ST_OK) rc = fail(ctx, RR_ERR_UNSUPPORTED, "rr_debug_align: window beyond the bit-vector scratch");
+  else {
+    if (res[0]) CK(cudaMemcpy(cigar, dc.p, res[0], cudaMemcpyDeviceToHost));
+    *cigar_len = res[0];
+    *edits = res[1];
+  }
+  dq.release(); dt.release(); dc.release(); dout.release();
+  return rc;
+}
+
+__global__ void rr_debug_rng_kernel(uint64_t seed, uint64_t first, uint32_t n, uint32_t* out) {
+  __shared__ uint32_t words[RNG_WORDS];
+  WarpRng rng;
+  rng.seed(seed, words, threadIdx.x & 31);
+  rng.cur = first;
+  for (uint32_t i = 0; i < n; ++i) {
+    uint32_t v = rng.next_u32();
+    if (threadIdx.x == 0) out[i] = v;
+  }
+}
+
+RR_API int rr_debug_rng_words(rr_ctx* ctx, uint64_t seed, uint64_t first, uint32_t n, uint32_t* out) {
+  if (!ctx || !out) return RR_ERR_ARG;
+  CK(cudaSetDevice(ctx->device));
+  DevBuf d;
+  ENSURE(d, (size_t)n * 4 + 16);
+  rr_debug_rng_kernel<<<1, 32, 0, ctx->stream>>>(seed, first, n, d.as<uint32_t>());
+  CK(cudaGetLastError());
+  ctx->launches += 1;
+  CK(cudaMemcpyAsync(out, d.p, (size_t)n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  d.release();
+  return RR_OK;
+}
+
+RR_API int rr_debug_fetch(rr_ctx* ctx, uint64_t i, int which, uint8_t* out, uint64_t cap, uint64_t* len) {
+  if (!ctx || !out || !len) return RR_ERR_ARG;
+  if (!ctx->ran || i >= ctx->n) return fail(ctx, RR_ERR_ARG, "rr_debug_fetch: no such read");
+  CK(cudaSetDevice(ctx->device));
+  uint64_t l = 0;
+  const DevBuf& lens = which == 0 ? ctx->d_raw_len : ctx->d_cig_len;
+  CK(cudaMemcpy(&l, lens.as<uint64_t>() + i, 8, cudaMemcpyDeviceToHost));
+  if (l > cap) return fail(ctx, RR_ERR_ARG, "rr_debug_fetch: buffer too small");
+  const uint8_t* src = which == 0 ? ctx->d_raw.as<uint8_t>() + ctx->h_raw_off[i] : ctx->d_cig.as<uint8_t>() + ctx->h_out_off[i];
+  if (l) CK(cudaMemcpy(out, src, l, cudaMemcpyDeviceToHost));
+  *len = l;
+  return RR_OK;
+}

@@ -1,0 +1,225 @@
+// rustyread_b200 — K6: quality::generate_quality (src/simulate/quality.rs:14-38) +
+// Quality::get_qscore (src/model/quality.rs:113-133), and K7a: packing of the sequences.
+//
+// get_qscore consumes exactly one u64 of the read's stream per non-'D' CIGAR position, so
+// position i with rank r (non-'D' positions before it) uses stream words q_cursor + 2r, +1.
+// A block walks one read in tiles: prefix-rank the tile, generate exactly the ChaCha blocks the
+// tile needs (one block per thread), then every thread samples its positions independently.
+//
+// The "strip one char from both ends until the window is known" fallback of get_qscore is
+// resolved once on the host into dense tables: for every odd length l <= max_k, a 4^l-entry
+// table (alphabet = X I D) -> distribution id.
+#pragma once
+#include "rr_device.cuh"
+
+namespace rr {
+
+constexpr int Q_THREADS = 256;
+constexpr int Q_PER_THREAD = 8;
+constexpr int Q_TILE = 2040;  // multiple of 8; 2 * 2040 + 15 words fit in 256 ChaCha blocks
+constexpr int Q_HALO = 8;     // (max_k - 1) / 2 <= 7
+
+struct QscoreModelDev {
+  uint32_t max_k;
+  const uint32_t* tab_off;   // indexed by window length l (odd) -> offset into tab
+  const uint16_t* tab;       // dist id, 0xFFFF = unknown
+  const uint32_t* dist_off;  // n_dist + 1
+  const uint8_t* scores;
+  const double* cum;         // per dist: partial sums, last = total
+  const double* scale;       // per dist
+};
+
+struct QscoreKernelParams {
+  QscoreModelDev Q;
+  const rr_desc* descs;
+  const uint32_t* order;
+  uint32_t n_reads;
+  uint32_t* queue;
+  const uint64_t* out_off;     // cigar arena offsets
+  const uint8_t* cig;
+  const uint64_t* cig_len;
+  const uint64_t* err_len;
+  const uint64_t* q_cursor;
+  const uint64_t* packed_off;  // where read i's quality string goes
+  uint8_t* qual;
+  uint32_t* status;
+};
+
+__device__ __forceinline__ uint32_t cigar_sym(uint8_t c) { return c == '=' ? 0u : c == 'X' ? 1u : c == 'I' ? 2u : 3u; }
+
+__global__ void __launch_bounds__(Q_THREADS) rr_qscore_kernel(const __grid_constant__ QscoreKernelParams P) {
+  __shared__ uint32_t s_words[Q_THREADS * 16];
+  __shared__ __align__(8) uint8_t s_cig[Q_HALO + Q_TILE + Q_HALO];
+  __shared__ uint32_t s_warp_sum[Q_THREADS / 32];
+  __shared__ uint32_t s_slot;
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const QscoreModelDev& Q = P.Q;
+  const uint32_t margin = (Q.max_k - 1) / 2;
+
+  for (;;) {
+    __syncthreads();
+    if (tid == 0) s_slot = atomicAdd(P.queue, 1u);
+    __syncthreads();
+    const uint32_t slot = s_slot;
+    if (slot >= P.n_reads) break;
+    const uint32_t ridx = P.order[slot];
+    if (P.status[ridx] != ST_OK) continue;
+    const uint64_t n = P.cig_len[ridx];
+    const uint8_t* cig = P.cig + P.out_off[ridx];
+    uint8_t* qual = P.qual + P.packed_off[ridx];
+    const uint64_t elen = P.err_len[ridx];
+    const uint64_t qcur = P.q_cursor[ridx];
+    uint32_t key[8];
+    chacha_key_from_u64(P.descs[ridx].seed, key);
+
+    uint64_t rank0 = 0;  // non-'D' positions before this tile
+    for (uint64_t t0 = 0; t0 < n; t0 += Q_TILE) {
+      const uint32_t tn = (uint32_t)min((uint64_t)Q_TILE, n - t0);
+      __syncthreads();
+      // stage the tile (+ halo) of the CIGAR
+      for (uint32_t x = tid; x < tn + 2 * Q_HALO; x += Q_THREADS) {
+        int64_t gi = (int64_t)t0 + (int64_t)x - Q_HALO;
+        s_cig[x] = (gi >= 0 && (uint64_t)gi < n) ? cig[gi] : 0;
+      }
+      __syncthreads();
+      // rank the non-'D' positions: 8 consecutive positions per thread
+      const uint32_t p0 = tid * Q_PER_THREAD;
+      uint32_t flags = 0;
+#pragma unroll
+      for (int x = 0; x < Q_PER_THREAD; ++x)
+        if (p0 + x < tn && s_cig[Q_HALO + p0 + x] != 'D') flags |= 1u << x;
+      uint32_t mine = __popc(flags);
+      uint32_t incl = mine;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        uint32_t y = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += y;
+      }
+      if (lane == 31) s_warp_sum[wid] = incl;
+      __syncthreads();
+      uint32_t wbase = 0, total = 0;
+#pragma unroll
+      for (int w = 0; w < Q_THREADS / 32; ++w) {
+        uint32_t s = s_warp_sum[w];
+        if (w < wid) wbase += s;
+        total += s;
+      }
+      const uint32_t excl = wbase + incl - mine;
+      // the ChaCha blocks holding words [qcur + 2 rank0, qcur + 2 (rank0 + total))
+      const uint64_t w_first = qcur + 2 * rank0;
+      const uint64_t b_first = w_first >> 4;
+      if (total) {
+        const uint64_t b_last = (w_first + 2 * (uint64_t)total - 1) >> 4;
+        if (b_first + (uint64_t)tid <= b_last) {
+          uint32_t out[16];
+          chacha12_block(key, b_first + (uint64_t)tid, out);
+#pragma unroll
+          for (int j = 0; j < 16; ++j) s_words[WarpRng::swz((uint32_t)tid * 16u + j)] = out[j];
+        }
+      }
+      __syncthreads();
+      uint32_t r = excl;
+#pragma unroll
+      for (int x = 0; x < Q_PER_THREAD; ++x) {
+        if (!(flags & (1u << x))) continue;
+        const uint64_t i = t0 + p0 + x;  // position in the CIGAR
+        // centred window, shrunk symmetrically at both ends (quality.rs:22-34)
+        uint32_t half;
+        if (i < margin) half = (uint32_t)i;
+        else if (i >= n - margin) half = (uint32_t)(n - i - 1);
+        else half = margin;
+        const uint32_t len = 2 * half + 1;
+        const uint8_t* wptr = s_cig + Q_HALO + p0 + x - half;
+        uint32_t code = 0;
+        for (uint32_t y = 0; y < len; ++y) code |= cigar_sym(wptr[y]) << (2 * y);
+        const uint32_t dist = Q.tab[Q.tab_off[len] + code];
+        uint8_t qv = '!';
+        if (dist == 0xFFFFu) {
+          P.status[ridx] = ST_QUAL;
+        } else {
+          const uint32_t woff = (uint32_t)(w_first + 2 * (uint64_t)r - (b_first << 4));
+          const uint64_t v = (uint64_t)s_words[WarpRng::swz(woff)] | ((uint64_t)s_words[WarpRng::swz(woff + 1)] << 32);
+          const uint32_t d0 = Q.dist_off[dist], nd = Q.dist_off[dist + 1] - d0;
+          const double chosen = u64_to_unit12(v) * Q.scale[dist] + 0.0;
+          uint32_t lo = 0, hi = nd - 1;  // partition_point over the first nd - 1 partial sums
+          while (lo < hi) {
+            uint32_t mid = (lo + hi) >> 1;
+            if (Q.cum[d0 + mid] <= chosen) lo = mid + 1; else hi = mid;
+          }
+          qv = Q.scores[d0 + lo] + 33;
+        }
+        const uint64_t qi = rank0 + r;
+        if (qi < elen) qual[qi] = qv;
+        ++r;
+      }
+      rank0 += total;
+    }
+    // mod.rs:284-287: the quality string is resized to the sequence length with '!'
+    for (uint64_t x = rank0 + tid; x < elen; x += Q_THREADS) qual[x] = '!';
+  }
+}
+
+// err arena -> packed sequence arena (both 16-byte aligned per read)
+struct PackKernelParams {
+  uint32_t n_reads;
+  const uint64_t* out_off;
+  const uint64_t* packed_off;
+  const uint64_t* err_len;
+  const uint8_t* err;
+  uint8_t* seq;
+};
+
+__global__ void __launch_bounds__(256) rr_pack_kernel(const __grid_constant__ PackKernelParams P) {
+  for (uint32_t r = blockIdx.x; r < P.n_reads; r += gridDim.x) {
+    const uint64_t n = P.err_len[r];
+    const uint4* src = reinterpret_cast<const uint4*>(P.err + P.out_off[r]);
+    uint4* dst = reinterpret_cast<uint4*>(P.seq + P.packed_off[r]);
+    const uint64_t nv = (n + 15) / 16;  // capacity is padded to 16 on both sides
+    for (uint64_t i = threadIdx.x; i < nv; i += blockDim.x) dst[i] = src[i];
+  }
+}
+
+// packed offsets: exclusive scan of round_up(err_len, 16); single block, n up to a few million
+__global__ void __launch_bounds__(1024) rr_scan_kernel(const uint64_t* __restrict__ err_len, const uint32_t* __restrict__ status,
+                                                        uint32_t n, uint32_t k, uint64_t* __restrict__ packed_off,
+                                                        uint64_t* __restrict__ totals /* [0] bytes, [1] bases, [2] failed */) {
+  __shared__ uint64_t s_part[1024];
+  __shared__ uint64_t s_bases[1024];
+  __shared__ uint64_t s_fail[1024];
+  const uint32_t tid = threadIdx.x;
+  const uint32_t per = (n + 1023) / 1024;
+  const uint32_t b = tid * per, e = min(n, b + per);
+  uint64_t sum = 0, bases = 0, fail = 0;
+  for (uint32_t i = b; i < e; ++i) {
+    uint64_t l = err_len[i];
+    sum += (l + 15) & ~15ULL;
+    if (l > 14 && l > 2ULL * k) bases += l - 2ULL * k;  // writer: mod.rs:192-208
+    fail += status[i] != ST_OK;
+  }
+  s_part[tid] = sum;
+  s_bases[tid] = bases;
+  s_fail[tid] = fail;
+  __syncthreads();
+  if (tid == 0) {
+    uint64_t acc = 0, ab = 0, af = 0;
+    for (int i = 0; i < 1024; ++i) {
+      uint64_t x = s_part[i];
+      s_part[i] = acc;
+      acc += x;
+      ab += s_bases[i];
+      af += s_fail[i];
+    }
+    packed_off[n] = acc;
+    totals[0] = acc;
+    totals[1] = ab;
+    totals[2] = af;
+  }
+  __syncthreads();
+  uint64_t off = s_part[tid];
+  for (uint32_t i = b; i < e; ++i) {
+    packed_off[i] = off;
+    off += (err_len[i] + 15) & ~15ULL;
+  }
+}
+
+}  // namespace rr

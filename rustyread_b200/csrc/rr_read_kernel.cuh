@@ -1,0 +1,393 @@
+// rustyread_b200 — the per-read kernel: assemble (K2) -> glitches + error walk (K3) with inline
+// alignment (K4) -> streamed stitch (K5).  See rr_device.cuh for the layout of the work.
+#pragma once
+#include "rr_device.cuh"
+
+namespace rr {
+
+__device__ __forceinline__ uint8_t complement(uint8_t c) {
+  // bio::alphabets::dna::complement (IUPAC aware, case preserving); used by Reference::new (src/references.rs:27)
+  switch (c) {
+    case 'A': return 'T'; case 'C': return 'G'; case 'G': return 'C'; case 'T': return 'A';
+    case 'a': return 't'; case 'c': return 'g'; case 'g': return 'c'; case 't': return 'a';
+    case 'Y': return 'R'; case 'R': return 'Y'; case 'K': return 'M'; case 'M': return 'K';
+    case 'D': return 'H'; case 'H': return 'D'; case 'V': return 'B'; case 'B': return 'V';
+    case 'y': return 'r'; case 'r': return 'y'; case 'k': return 'm'; case 'm': return 'k';
+    case 'd': return 'h'; case 'h': return 'd'; case 'v': return 'b'; case 'b': return 'v';
+    default: return c;  // W, S, N and anything unknown map to themselves
+  }
+}
+
+// Adapter::get_start / get_end (src/model/adapter.rs:64-93): Bernoulli(rate), then a Beta-distributed
+// prefix of the adapter.  Returns the number of bytes appended.
+__device__ uint32_t add_adapter(WarpRng& rng, const DeviceModels& M, bool end_side, uint8_t* dst, int lane) {
+  double rate = end_side ? M.end_rate : M.start_rate;
+  int has = end_side ? M.has_end : M.has_start;
+  if (!rng.gen_bool(rate) || !has) return 0;
+  uint32_t alen = end_side ? M.end_len : M.start_len;
+  const uint8_t* a = M.adapter_bytes + (end_side ? M.start_len : 0);
+  double frac = beta_sample(end_side ? M.end_beta : M.start_beta, rng);
+  uint32_t n = (uint32_t)round((double)alen * frac);
+  if (n > alen) n = alen;
+  for (uint32_t i = lane; i < n; i += 32) dst[i] = a[i];
+  return n;
+}
+
+// add_fragment (src/simulate/mod.rs:295-339).  `tmp` = 8 bytes of shared memory.
+__device__ uint64_t add_fragment(WarpRng& rng, const DeviceModels& M, uint32_t type, uint32_t ref_idx, uint32_t strand,
+                                 uint64_t start, uint64_t end, uint8_t* dst, uint8_t* tmp, int lane) {
+  if (type == RR_JUNK) {  // mod.rs:310-317
+    uint64_t unit = rng.gen_range_u64(1, 5);
+    __syncwarp();
+    rng.random_seq(unit, tmp);
+    __syncwarp();
+    uint64_t total = (end / unit) * unit;
+    for (uint64_t i = lane; i < total; i += 32) dst[i] = tmp[i % unit];
+    return total;
+  }
+  if (type == RR_RANDOM) {  // mod.rs:319-324
+    rng.random_seq(end, dst);
+    return end;
+  }
+  // mod.rs:326-339 — `revcomp` is indexed with the same coordinates as `seq`
+  const uint64_t r0 = M.ref_off[ref_idx];
+  const uint64_t rl = M.ref_off[ref_idx + 1] - r0;
+  const uint8_t* ref = M.ref_bytes + r0;
+  const bool rc = strand == RR_MINUS;
+  uint64_t n1, n2 = 0;
+  if (start < end) n1 = end - start;
+  else if (M.ref_circ[ref_idx]) { n1 = rl - start; n2 = end; }
+  else return 0;
+  if (!rc) {
+    for (uint64_t i = lane; i < n1; i += 32) dst[i] = ref[start + i];
+    for (uint64_t i = lane; i < n2; i += 32) dst[n1 + i] = ref[i];
+  } else {
+    for (uint64_t i = lane; i < n1; i += 32) dst[i] = complement(ref[rl - 1 - (start + i)]);
+    for (uint64_t i = lane; i < n2; i += 32) dst[n1 + i] = complement(ref[rl - 1 - i]);
+  }
+  return n1 + n2;
+}
+
+// State of `changes.last()` plus the streamed stitch of sequence() (src/simulate/error.rs:219-246).
+// A Change only ever grows by appending to seq / cigar (merge, error.rs:105-152), and only the last
+// one can change, so err / CIGAR are written once, in order, as the walk proceeds.
+struct Stitch {
+  const uint8_t* raw;
+  uint64_t L;
+  uint8_t* err;
+  uint8_t* cig;
+  uint64_t cap;
+  uint64_t err_len, cig_len;
+  uint64_t pos_in_raw;   // sequence(): end of the last emitted change
+  uint64_t real_edit;
+  bool has_last, l_emit;
+  uint64_t lb, le, lseq_len, ledit;
+  int status;
+};
+
+__device__ __forceinline__ void st_finalize_last(Stitch& S) {
+  if (S.has_last && S.l_emit) {
+    S.real_edit += S.ledit;
+    S.pos_in_raw = S.le;
+  }
+}
+
+__device__ __forceinline__ bool st_reserve(Stitch& S, uint64_t n_err, uint64_t n_cig) {
+  if (S.err_len + n_err > S.cap || S.cig_len + n_cig > S.cap) {
+    S.status = ST_OUT_OVERFLOW;
+    return false;
+  }
+  return true;
+}
+
+__device__ void st_emit_gap(Stitch& S, uint64_t upto, int lane) {  // raw[pos_in_raw..upto) copied, '=' in the CIGAR
+  if (upto <= S.pos_in_raw) return;
+  uint64_t n = upto - S.pos_in_raw;
+  if (!st_reserve(S, n, n)) return;
+  const uint8_t* src = S.raw + S.pos_in_raw;
+  uint8_t* de = S.err + S.err_len;
+  uint8_t* dc = S.cig + S.cig_len;
+  for (uint64_t i = lane; i < n; i += 32) {
+    de[i] = src[i];
+    dc[i] = '=';
+  }
+  S.err_len += n;
+  S.cig_len += n;
+}
+
+__device__ void st_emit_seq(Stitch& S, const uint8_t* q, uint64_t n, int lane) {
+  if (!st_reserve(S, n, 0)) return;
+  uint8_t* de = S.err + S.err_len;
+  for (uint64_t i = lane; i < n; i += 32) de[i] = q[i];
+  S.err_len += n;
+}
+
+// AbsChanges::add_change (src/simulate/error.rs:173-193) with contain / overlap / merge /
+// update_align (error.rs:83-164).  Returns the edit count to subtract from the target.
+__device__ uint64_t add_change(Stitch& S, WarpSmem* ws, const ReadKernelParams& P, uint32_t gwarp, uint64_t ob, uint64_t oe,
+                               const uint8_t* oseq, uint64_t olen, int lane) {
+  if (S.has_last) {
+    const uint64_t l_end_err = S.lb + S.lseq_len;
+    const uint64_t o_end_err = ob + olen;
+    if (oe <= l_end_err || oe <= S.le || o_end_err <= l_end_err) return 0;  // contain
+    if (ob < l_end_err || ob < S.le) {                                       // overlap -> merge
+      uint64_t es, old_end = S.le;
+      if (ob < l_end_err) {
+        uint64_t ovl = l_end_err - ob;
+        es = ovl;  // olen > ovl holds because the change is not contained
+        S.le = S.le + oe - ob - ovl;
+      } else {
+        es = 0;
+        S.le = ob + olen;
+      }
+      uint64_t rs, re;
+      if (S.le < S.L - 1) {
+        if (old_end < S.le) { rs = old_end; re = S.le; } else { rs = S.le; re = old_end; }
+      } else { rs = old_end; re = S.L; }
+      if (rs > re || re > S.L || es > olen) { S.status = ST_REF_PANIC; return 0; }
+      uint64_t add = olen - es;
+      S.lseq_len += add;
+      if (S.l_emit) st_emit_seq(S, oseq + es, add, lane);
+      if (S.status) return 0;
+      AlignOut a = warp_align(ws, P, gwarp, oseq + es, (uint32_t)add, S.raw + rs, (uint32_t)(re - rs),
+                              S.l_emit ? S.cig + S.cig_len : nullptr, S.cap - S.cig_len, lane);
+      if (a.status) { S.status = a.status; return 0; }
+      if (S.l_emit) S.cig_len += a.n_ops;
+      S.ledit += a.edits;
+      return a.edits;
+    }
+  }
+  // push a new change (update_align: error.rs:155-164)
+  st_finalize_last(S);
+  uint64_t e = oe > S.L ? S.L : oe;
+  if (ob > e) { S.status = ST_REF_PANIC; return 0; }
+  bool emit = ob >= S.pos_in_raw;  // sequence(): `if change.begin() < pos_in_raw { continue }`
+  if (emit) {
+    st_emit_gap(S, ob, lane);
+    st_emit_seq(S, oseq, olen, lane);
+    if (S.status) return 0;
+  }
+  AlignOut a = warp_align(ws, P, gwarp, oseq, (uint32_t)olen, S.raw + ob, (uint32_t)(e - ob),
+                          emit ? S.cig + S.cig_len : nullptr, S.cap - S.cig_len, lane);
+  if (a.status) { S.status = a.status; return 0; }
+  if (emit) S.cig_len += a.n_ops;
+  S.has_last = true;
+  S.l_emit = emit;
+  S.lb = ob;
+  S.le = oe;
+  S.lseq_len = olen;
+  S.ledit = a.edits;
+  return a.edits;
+}
+
+// Error::add_errors_to_kmer (src/model/error.rs:93-107) / random_error (error.rs:116-135).
+// Writes the altered k-mer to ws->alt, returns its length.
+__device__ uint32_t make_alt(WarpRng& rng, const DeviceModels& M, WarpSmem* ws, const uint8_t* kmer, int lane) {
+  const uint32_t k = M.k;
+  __syncwarp();
+  if (M.em_index) {
+    // 2-bit code of the k-mer; any byte outside ACGT misses the table
+    uint32_t part = 0, bad = 0;
+    if ((uint32_t)lane < k) {
+      uint8_t c = kmer[lane];
+      uint32_t s = c == 'A' ? 0u : c == 'C' ? 1u : c == 'G' ? 2u : c == 'T' ? 3u : 4u;
+      bad = s > 3u;
+      part = (s & 3u) << (2 * (k - 1 - lane));
+    }
+    uint32_t code = __reduce_or_sync(0xffffffffu, part);
+    bool anybad = __any_sync(0xffffffffu, bad);
+    int key = anybad ? -1 : M.em_index[code];
+    if (key >= 0) {
+      uint32_t a0 = M.em_alt_begin[key], a1 = M.em_alt_begin[key + 1];
+      uint32_t na = a1 - a0;
+      double chosen = u64_to_unit12(rng.next_u64()) * M.em_scale[key] + 0.0;
+      // WeightedIndex: number of partial sums <= chosen among the first na - 1
+      uint32_t idx = 0;
+      for (uint32_t b = 0; b + 1 < na; b += 32) {
+        uint32_t i = b + lane;
+        bool le = (i + 1 < na) && (M.em_cum[a0 + i] <= chosen);
+        idx += __popc(__ballot_sync(0xffffffffu, le));
+      }
+      uint32_t o0 = M.em_alt_off[a0 + idx], o1 = M.em_alt_off[a0 + idx + 1];
+      uint32_t n = o1 - o0;
+      for (uint32_t i = lane; i < n; i += 32) ws->alt[i] = M.em_alt_bytes[o0 + i];
+      __syncwarp();
+      return n;
+    }
+  }
+  uint32_t ep = (uint32_t)rng.gen_range_u64(0, k - 1);
+  uint32_t kind = rng.gen_range_u32(1, 3);  // 1 substitution, 2 insertion, 3 deletion
+  uint8_t at = kmer[ep];
+  uint8_t nb = 0;
+  if (kind == 1) nb = rng.random_base_diff(at);
+  else if (kind == 2) nb = rng.random_base();
+  uint32_t n = kind == 1 ? k : (kind == 2 ? k + 1 : k - 1);
+  if ((uint32_t)lane < n) {
+    uint32_t i = lane;
+    uint8_t c;
+    if (kind == 1) c = (i == ep) ? nb : kmer[i];
+    else if (kind == 2) c = (i < ep) ? kmer[i] : (i == ep ? nb : kmer[i - 1]);
+    else c = (i < ep) ? kmer[i] : kmer[i + 1];
+    ws->alt[i] = c;
+  }
+  __syncwarp();
+  return n;
+}
+
+__device__ void process_read(const ReadKernelParams& P, WarpSmem* ws, uint32_t gwarp, uint32_t ridx, int lane) {
+  const DeviceModels& M = P.M;
+  const rr_desc d = P.descs[ridx];
+  const uint32_t k = M.k;
+  WarpRng rng;
+  rng.seed(d.seed, ws->rng, lane);
+
+  // ---- K2: raw fragment (src/simulate/mod.rs:243-271) ----
+  uint8_t* raw = P.raw + P.raw_off[ridx];
+  uint64_t L = 0;
+  rng.random_seq(k, raw);
+  L += k;
+  L += add_adapter(rng, M, false, raw + L, lane);
+  L += add_fragment(rng, M, d.type, d.ref_idx, d.strand, d.start, d.end, raw + L, ws->alt, lane);
+  if (d.has_chimera) {
+    if (rng.gen_bool(0.25)) L += add_adapter(rng, M, true, raw + L, lane);   // CHIMERA_END_ADAPTER_CHANCE, lib.rs:13
+    if (rng.gen_bool(0.25)) L += add_adapter(rng, M, false, raw + L, lane);  // CHIMERA_START_ADAPTER_CHANCE, lib.rs:12
+    L += add_fragment(rng, M, d.ctype, d.cref_idx, d.cstrand, d.cstart, d.cend, raw + L, ws->alt, lane);
+  }
+  L += add_adapter(rng, M, true, raw + L, lane);
+  rng.random_seq(k, raw + L);
+  L += k;
+  __syncwarp();
+
+  Stitch S;
+  S.raw = raw;
+  S.L = L;
+  S.err = P.err + P.out_off[ridx];
+  S.cig = P.cig + P.out_off[ridx];
+  S.cap = P.out_off[ridx + 1] - P.out_off[ridx];
+  S.err_len = S.cig_len = 0;
+  S.pos_in_raw = 0;
+  S.real_edit = 0;
+  S.has_last = false;
+  S.l_emit = false;
+  S.lb = S.le = S.lseq_len = S.ledit = 0;
+  S.status = ST_OK;
+
+  // ---- K3: error::sequence (src/simulate/error.rs:201-217) ----
+  double target = (1.0 - d.identity) * (double)L;  // number_of_edit, error.rs:196-198
+
+  // add_glitches (error.rs:250-264): positions, skips and inserted bases are drawn up front
+  GlitchRec* grec = P.sc_grec + (uint64_t)gwarp * P.sc_grec_cap;
+  uint8_t* gseq = P.sc_gseq + (uint64_t)gwarp * P.sc_gseq_cap;
+  uint32_t ng = 0;
+  if (M.has_distance) {
+    uint64_t position = 0, gbytes = 0;
+    for (;;) {
+      uint64_t begin = geometric_sample(M.g_dist, rng);
+      uint64_t end = begin + geometric_sample(M.g_skip, rng);
+      uint64_t size = geometric_sample(M.g_size, rng);
+      if (gbytes + size > P.sc_gseq_cap || ng >= P.sc_grec_cap) { S.status = ST_GLITCH_OVERFLOW; break; }
+      __syncwarp();
+      rng.random_seq(size, gseq + gbytes);
+      position += begin;
+      if (position > L || position + end > L) break;
+      if (lane == 0) {
+        GlitchRec g;
+        g.begin = position;
+        g.end = position + (end - begin);
+        g.seq_off = (uint32_t)gbytes;
+        g.seq_len = (uint32_t)size;
+        grec[ng] = g;
+      }
+      ++ng;
+      gbytes += size;
+    }
+    __syncwarp();
+  }
+
+  // add_error (error.rs:267-302): one Bernoulli(target / (L - pos)) per position.  32 positions are
+  // tried at once against the current target; the first lane with an event wins.
+  if (S.status == ST_OK) {
+    const uint64_t nlim = L - k;
+    uint64_t pos = 0;
+    uint32_t g = 0;
+    uint64_t gbegin = ng ? grec[0].begin : ~0ULL;
+    bool glitch_checked = false;
+    while (pos < nlim) {
+      rng.need(64);
+      const uint64_t pi = pos + (uint64_t)lane;
+      const bool inb = pi < nlim;
+      const double rem = (double)(L - pi);
+      const bool brk = target < 0.0 || target > rem;
+      const bool gl = (g < ng) && (pi == gbegin) && !(lane == 0 && glitch_checked);
+      const double p = target / rem;
+      const bool one = (p == 1.0);
+      const uint64_t v = rng.peek64(rng.cur + 2 * (uint64_t)lane);
+      const bool hit = one || v < bernoulli_threshold(p);
+      const uint32_t m_any = __ballot_sync(0xffffffffu, !inb || gl || brk || hit);
+      if (m_any == 0) {
+        pos += 32;
+        rng.cur += 64;
+        glitch_checked = false;
+        continue;
+      }
+      const int f = __ffs(m_any) - 1;
+      const uint32_t fl = (inb ? 1u : 0u) | (gl ? 2u : 0u) | (brk ? 4u : 0u) | (one ? 8u : 0u);
+      const uint32_t ff = __shfl_sync(0xffffffffu, fl, f);
+      if (f > 0) {
+        pos += (uint64_t)f;
+        rng.cur += 2 * (uint64_t)f;
+        glitch_checked = false;
+      }
+      if (!(ff & 1u)) break;  // pos == L - k
+      if (ff & 2u) {          // glitch due at pos (error.rs:282-287)
+        GlitchRec gr = grec[g];
+        target -= (double)add_change(S, ws, P, gwarp, gr.begin, gr.end, gseq + gr.seq_off, gr.seq_len, lane);
+        ++g;
+        gbegin = (g < ng) ? grec[g].begin : ~0ULL;
+        glitch_checked = true;
+        if (S.status) break;
+        continue;  // same pos again, with the new target, glitch check done
+      }
+      if (ff & 4u) break;  // error.rs:289-291
+      if (!(ff & 8u)) rng.cur += 2;
+      uint32_t alen = make_alt(rng, M, ws, raw + pos, lane);
+      target -= (double)add_change(S, ws, P, gwarp, pos, pos + k, ws->alt, alen, lane);
+      if (S.status) break;
+      if (target < 0.0 || target > (double)(L - pos)) break;  // error.rs:298-300
+      pos += 1;
+      glitch_checked = false;
+    }
+  }
+
+  // ---- K5: tail of the stitch (error.rs:241-246) ----
+  if (S.status == ST_OK) {
+    st_finalize_last(S);
+    if (S.pos_in_raw < L) st_emit_gap(S, L, lane);
+  }
+  __syncwarp();
+  if (lane == 0) {
+    P.raw_len[ridx] = L;
+    P.err_len[ridx] = S.status ? 0 : S.err_len;
+    P.cig_len[ridx] = S.status ? 0 : S.cig_len;
+    P.q_cursor[ridx] = rng.cur;
+    P.real_id[ridx] = (1.0 - ((double)S.real_edit / (double)L)) * 100.0;  // error.rs:246, mod.rs:289
+    P.status[ridx] = (uint32_t)S.status;
+  }
+}
+
+__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, 4) rr_read_kernel(const __grid_constant__ ReadKernelParams P) {
+  __shared__ WarpSmem smem[WARPS_PER_BLOCK];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t gwarp = blockIdx.x * WARPS_PER_BLOCK + warp;
+  WarpSmem* ws = &smem[warp];
+  for (;;) {
+    uint32_t slot = 0;
+    if (lane == 0) slot = atomicAdd(P.queue, 1u);
+    slot = __shfl_sync(0xffffffffu, slot, 0);
+    if (slot >= P.n_reads) break;
+    process_read(P, ws, gwarp, P.order[slot], lane);
+    __syncwarp();
+  }
+}
+
+}  // namespace rr

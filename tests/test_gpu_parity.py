@@ -1,0 +1,333 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the CPU oracle and the reference's goldens.
+Bit-exact: every byte of every sequence and quality string, and every f64 identity, must be equal."""
+import random
+
+import numpy as np
+import pytest
+
+import helpers
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def rr():
+    import rustyread_b200
+
+    return rustyread_b200
+
+
+@pytest.fixture(scope="module")
+def ctx(rr):
+    c = rr.Context(0)
+    yield c
+    c.close()
+
+
+# ---- K1: ChaCha12 word stream --------------------------------------------------------------------
+@pytest.mark.parametrize("seed,first,n", [(42, 0, 2000), (0, 0, 64), (2 ** 64 - 1, 0, 100), (17195042692806716983, 12345, 1500), (7, 511, 3)])
+def test_rng_words(orc, ctx, seed, first, n):
+    want = np.zeros(n, dtype=np.uint32)
+    orc.lib.orc_rng_words_block(seed, first, n, want.ctypes.data)
+    got = ctx.debug_rng_words(seed, first, n)
+    assert np.array_equal(got, want)
+
+
+# ---- K4: alignment -----------------------------------------------------------------------------------
+def test_align_goldens(ctx, goldens):  # src/alignment.rs:47-86
+    for q, t, e, cigar in goldens["alignment.align"]:
+        assert ctx.debug_align(q.encode(), t.encode()) == (e, cigar)
+
+
+def test_align_glitch_goldens(orc, ctx, goldens):  # windows of src/simulate/error.rs:646-713
+    g = goldens["simulate.error.glitches"]
+    raw = orc.rng(42).random_seq(g["raw_len"])
+    for c in g["truth"]:
+        got = ctx.debug_align(c["seq"].encode(), raw[c["begin"]:c["end"]])
+        assert got == (c["edit_distance"], c["cigar"])
+
+
+@pytest.mark.parametrize("mmax,nmax,alphabet,count", [
+    (12, 12, "ACGT", 400),     # k-mer sized windows (fast path)
+    (40, 64, "AC", 200),       # low-entropy: many ties
+    (127, 64, "ACGT", 60),     # fast-path limits
+    (128, 65, "ACGT", 40),     # just past the fast path
+    (300, 300, "ACGTN", 40),   # glitch-sized windows, multi-word rows, non-ACGT bytes
+    (900, 1100, "ACGT", 6),
+    (5, 2048, "ACGT", 4),
+    (1500, 3, "ACGT", 4),
+])
+def test_align_fuzz(orc, ctx, mmax, nmax, alphabet, count):
+    rnd = random.Random(mmax * 7919 + nmax)
+    for it in range(count):
+        m = rnd.randint(0, mmax) if it % 5 else mmax
+        n = rnd.randint(0, nmax) if it % 7 else nmax
+        q = "".join(rnd.choice(alphabet) for _ in range(m))
+        if it % 3 == 0 and m:  # related sequences, like a real error window
+            t = list(q)
+            for _ in range(rnd.randint(0, 3)):
+                op = rnd.choice("sid")
+                p = rnd.randrange(len(t) + 1)
+                if op == "s" and p < len(t):
+                    t[p] = rnd.choice(alphabet)
+                elif op == "i":
+                    t.insert(p, rnd.choice(alphabet))
+                elif op == "d" and p < len(t):
+                    del t[p]
+            t = "".join(t)[:nmax]
+        else:
+            t = "".join(rnd.choice(alphabet) for _ in range(n))
+        assert ctx.debug_align(q.encode(), t.encode()) == orc.align(q, t), (q, t)
+
+
+def test_align_too_large_fails_loudly(rr, ctx):
+    with pytest.raises(rr.RRError):
+        ctx.debug_align(b"A" * 10, b"C" * 3000)
+
+
+# ---- full reads: the reference's own 20-read golden --------------------------------------------------------
+def test_produce_read_golden(orc, goldens):  # src/simulate/mod.rs:433-919
+    spec = dict(length=(8.0, 2.0), identity=(85.0, 95.0, 5.0), adapter=("TACGTATTGCT", "TACGTATTGCT", 90.0, 60.0, 50.0, 20.0),
+                glitch=(50.0, 5.0, 5.0), rates=(10.0, 10.0, 25.0), adjusted=False)
+    w, ctx, _ = helpers.make_pair(orc, goldens["simulate.FASTA"], spec)
+    w.feed(10_000, 20)
+    d, ident, _ = w.items()
+    import rustyread_b200.capi as capi
+
+    batch = ctx.generate(capi.descs_from_oracle_items(d, ident))
+    truth = goldens["simulate.produce_read"]
+    for i, (desc, wseq, wqual) in enumerate(truth):
+        s, q = batch.read(i)
+        assert list(s) == wseq, i
+        assert list(q) == wqual, i
+        assert batch.real_identity[i] == float(desc["identity"]["f64"]), i
+    w.generate(threads=2)
+    helpers.compare_batch(w, batch, ctx)
+    ctx.close()
+
+
+def _run_pair(orc, fasta, spec, target, max_items=0, threads=8):
+    import rustyread_b200.capi as capi
+
+    w, ctx, s = helpers.make_pair(orc, fasta, spec)
+    n = w.feed(target, max_items)
+    d, ident, _ = w.items()
+    batch = ctx.generate(capi.descs_from_oracle_items(d, ident))
+    w.generate(threads=threads)
+    helpers.compare_batch(w, batch, ctx)
+    return w, ctx, batch, n
+
+
+def test_shape_5mbp_golden(orc, goldens):  # src/simulate/mod.rs:922-1023 (58 reads, 1 048 243 bases)
+    import ctypes as C
+    import math
+
+    w0 = orc.workload(42)
+    w0.set_length(18200.0, 15500.0)
+    rh = w0.rng_handle()
+    parts = []
+    for n in (5_000_000, 80_000, 75_000):
+        out = (C.c_uint8 * n)()
+        orc.lib.orc_random_seq(rh, n, out)
+        parts.append(">%s\n%s\n" % ("{:_}".format(n), bytes(out).decode()))
+    fasta = "".join(parts)
+    # the reference test draws the contigs from the same rng that then feeds the run: replay that state
+    import rustyread_b200 as rrm
+    import rustyread_b200.capi as capi
+
+    w0.set_references(fasta, adjusted=True)
+    w0.set_identity(87.0, 100.0, 9.0)
+    w0.set_adapter("TACGTATTGCT", "TACGTATTGCT", 90.0, 60.0, 50.0, 20.0)
+    w0.set_error_model(None)
+    w0.set_qscore_model("random")
+    w0.set_glitch(50.0, 5.0, 5.0)
+    w0.set_rates(1.0, 1.0, 1.0)
+    n = w0.feed(1_000_000)
+    d, ident, _ = w0.items()
+    ctx = rrm.Context(0)
+    refs = w0.refs()
+    ctx.set_references([r["seq"] for r in refs], [r["circular"] for r in refs])
+    ctx.set_error_model_random(7)
+    ctx.set_qscore_model_random()
+    ctx.set_adapter(b"TACGTATTGCT", b"TACGTATTGCT", 90.0, 60.0, 50.0, 20.0)
+    ctx.set_glitch(50.0, 5.0, 5.0)
+    batch = ctx.generate(capi.descs_from_oracle_items(d, ident))
+    lengths = [float(x) for x in batch.lengths]
+    sum_len = 0.0
+    for x in lengths:
+        sum_len += x
+    sum_id = 0.0
+    for x in batch.real_identity:
+        sum_id += float(x)
+    avg_id = sum_id / n
+    acc = 0.0
+    for x in batch.real_identity:
+        acc += (float(x) - avg_id) ** 2.0
+    want = goldens["simulate.shape"]
+    assert [sum_len, sum_len / n, math.sqrt(sum_len / n), sum_id, avg_id, math.sqrt(acc / n)] == want
+    w0.generate(threads=8)
+    helpers.compare_batch(w0, batch, ctx)
+    ctx.close()
+
+
+# ---- BASELINE.json configs at sizes the oracle finishes in seconds ----------------------------------------------
+def test_config1_default(orc):
+    fasta = helpers.random_fasta(orc, [400_000])
+    _, ctx, batch, n = _run_pair(orc, fasta, {}, 4_000_000)
+    assert n > 150
+    ctx.close()
+
+
+def test_config4_ultralong_low_identity(orc):
+    fasta = helpers.random_fasta(orc, [600_000])
+    spec = dict(length=(50000.0, 40000.0), identity=(75.0, 90.0, 8.0), glitch=(2000.0, 50.0, 50.0), rates=(1.0, 1.0, 5.0))
+    _, ctx, batch, n = _run_pair(orc, fasta, spec, 6_000_000)
+    assert n > 60
+    ctx.close()
+
+
+def test_config5_plasmids_divergent(orc):
+    rnd = random.Random(5)
+    contigs = [int(2000 * (25 ** rnd.random())) for _ in range(60)]
+    fasta = helpers.random_fasta(orc, contigs, circular=set(range(60)), depth={3: "2.5", 7: "0.5"})
+    spec = dict(rates=(10.0, 10.0, 1.0), small_plasmid_bias=True, length=(6000.0, 5000.0))
+    _, ctx, batch, n = _run_pair(orc, fasta, spec, 3_000_000)
+    assert n > 300
+    ctx.close()
+
+
+def test_mixed_linear_circular_chimeras(orc):
+    fasta = helpers.random_fasta(orc, [120_000, 3_000, 50_000, 800, 20_000], circular={1, 3, 4}, depth={2: "3"})
+    spec = dict(rates=(5.0, 5.0, 30.0), length=(4000.0, 3500.0), identity=(80.0, 99.0, 10.0), glitch=(500.0, 30.0, 20.0))
+    _, ctx, batch, n = _run_pair(orc, fasta, spec, 2_000_000)
+    ctx.close()
+
+
+def test_file_models_fixtures(orc, goldens):
+    # the two inline model fixtures of the reference (src/model/error.rs:156, src/model/quality.rs:146-150)
+    fasta = "".join(">c%d\n%s\n" % (i, "ACAGTTG" * (3000 + 100 * i)) for i in range(3)) + helpers.random_fasta(orc, [50_000])
+    spec = dict(error_model=goldens["model.error.MODEL"], qscore_model=goldens["model.quality.MODEL"], length=(3000.0, 2500.0))
+    _, ctx, batch, n = _run_pair(orc, fasta, spec, 1_500_000)
+    ctx.close()
+
+
+def _synthetic_models(k=7, seed=9):
+    rnd = random.Random(seed)
+    lines = []
+    for code in range(4 ** k):
+        if rnd.random() < 0.25:
+            continue  # a quarter of the k-mers miss the table -> random_error
+        kmer = "".join("ACGT"[(code >> (2 * (k - 1 - i))) & 3] for i in range(k))
+        alts, total = [], 0.0
+        na = rnd.randint(1, 25)
+        for _ in range(na):
+            a = list(kmer)
+            for _ in range(rnd.randint(1, 3)):
+                op = rnd.choice("sid")
+                p = rnd.randrange(len(a)) if a else 0
+                if op == "s" and a:
+                    a[p] = rnd.choice("ACGT")
+                elif op == "i":
+                    a.insert(p, rnd.choice("ACGT"))
+                elif a:
+                    del a[p]
+            p_ = round(rnd.random() * 0.9 / na, 6)
+            total += p_
+            alts.append("%s,%s" % ("".join(a), repr(p_)))
+        lines.append("%s,%s;%s;" % (kmer, repr(round(max(0.0, 0.05), 6)), ";".join(alts)))
+    error_text = "\n".join(lines) + "\n"
+    q = ["overall;1000;" + ",".join("%d:%s" % (s, 0.01) for s in range(1, 40)) + ","]
+    seen = set()
+
+    def add(c):
+        if c in seen:
+            return
+        seen.add(c)
+        n = rnd.randint(3, 45)
+        scores = rnd.sample(range(1, 60), n)
+        q.append("%s;%d;%s," % (c, rnd.randint(1, 10 ** 6), ",".join("%d:%s" % (s, repr(round(rnd.random(), 6) + 1e-6)) for s in scores)))
+
+    for c in "=XI":
+        add(c)
+    for l in (3, 5, 7, 9):
+        for _ in range({3: 40, 5: 200, 7: 600, 9: 1500}[l]):
+            w = [rnd.choice("====XID") for _ in range(l)]
+            if w[l // 2] == "D":
+                w[l // 2] = "="
+            add("".join(w))
+    add("=" * 9)
+    return error_text, "\n".join(q) + "\n"
+
+
+def test_synthetic_badread_scale_models(orc):
+    error_text, qscore_text = _synthetic_models()
+    fasta = helpers.random_fasta(orc, [300_000])
+    spec = dict(error_model=error_text, qscore_model=qscore_text, length=(8000.0, 7000.0))
+    _, ctx, batch, n = _run_pair(orc, fasta, spec, 2_500_000)
+    ctx.close()
+
+
+def test_ideal_qscore_and_no_glitch_no_adapter(orc):
+    fasta = helpers.random_fasta(orc, [200_000])
+    spec = dict(qscore_model="ideal", glitch=(0.0, 0.0, 0.0), adapter=("", "", 0.0, 0.0, 0.0, 0.0), rates=(0.0, 0.0, 0.0),
+                length=(5000.0, 0.0), identity=(90.0, 90.0, 5.0))
+    _, ctx, batch, n = _run_pair(orc, fasta, spec, 1_000_000)
+    ctx.close()
+
+
+def test_tiny_and_ragged_reads(orc, goldens):
+    # reads of a handful of bases (the writer's `len <= 14` filter lives above this boundary)
+    spec = dict(length=(3.0, 2.0), adapter=("TACGTATTGCT", "TACGTATTGCT", 100.0, 60.0, 100.0, 20.0), glitch=(10.0, 3.0, 3.0),
+                rates=(20.0, 20.0, 50.0), adjusted=False)
+    _, ctx, batch, n = _run_pair(orc, goldens["simulate.FASTA"], spec, 3_000, threads=2)
+    assert n > 200
+    ctx.close()
+
+
+def test_run_is_repeatable_and_staged_api(orc):
+    import rustyread_b200.capi as capi
+
+    fasta = helpers.random_fasta(orc, [100_000])
+    w, ctx, s = helpers.make_pair(orc, fasta, {})
+    w.feed(500_000)
+    d, ident, _ = w.items()
+    descs = capi.descs_from_oracle_items(d, ident)
+    ctx.upload(descs)
+    ctx.run()
+    a = ctx.download()
+    sa, la = a.seq.copy(), a.lengths.copy()
+    l0 = ctx.kernel_launches()
+    ctx.run()
+    b = ctx.download()
+    assert ctx.kernel_launches() - l0 == 4
+    assert np.array_equal(la, b.lengths) and np.array_equal(sa[:a.total_bytes], b.seq[:b.total_bytes])
+    ms = ctx.last_run_ms()
+    assert ms["total"] > 0 and ms["read_kernel"] > 0
+    assert ctx.last_run_bases() == int(sum(int(x) - 14 for x in la if x > 14))
+    ctx.close()
+
+
+def test_invalid_inputs_fail_loudly(rr, orc):
+    import rustyread_b200.capi as capi
+
+    ctx = rr.Context(0)
+    d = np.zeros(1, dtype=capi.DESC_DTYPE)
+    with pytest.raises(rr.RRError):
+        ctx.generate(d)  # models not set
+    ctx.set_references([b"ACGT" * 10], [False])
+    ctx.set_error_model_random(7)
+    ctx.set_qscore_model_random()
+    ctx.set_adapter(b"", b"", 0.0, 0.0, 0.0, 0.0)
+    ctx.set_glitch(0.0, 0.0, 0.0)
+    d["ref_idx"] = 3
+    d["end"] = 5
+    d["identity"] = 0.9
+    with pytest.raises(rr.RRError):
+        ctx.generate(d)  # ref_idx out of range
+    d["ref_idx"] = 0
+    d["end"] = 500
+    with pytest.raises(rr.RRError):
+        ctx.generate(d)  # slice past the contig: the reference panics
+    with pytest.raises(rr.RRError):
+        ctx.set_qscore_model(1, [(b"=", [1], [1.0])])  # missing X / I
+    ctx.close()
