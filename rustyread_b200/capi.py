@@ -90,6 +90,7 @@ class Batch:
 
     def __init__(self, b):
         n = int(b.n_reads)
+        self.struct = b
         self.n = n
         self.k = int(b.k)
         self.total_bytes = int(b.total_bytes)
@@ -270,3 +271,146 @@ def descs_from_oracle_items(d12, identity):
     out["seed"] = d12[:, 11]
     out["identity"] = identity
     return out
+
+
+# ---------------------------------------------------------------------------------------------------
+# host side of `rustyread simulate` (include/rustyread_b200_host.h)
+# ---------------------------------------------------------------------------------------------------
+class rr_sim_params(C.Structure):
+    _fields_ = [("seed", C.c_uint64), ("length_mean", C.c_double), ("length_stdev", C.c_double),
+                ("identity_mean", C.c_double), ("identity_max", C.c_double), ("identity_stdev", C.c_double),
+                ("start_adapter_seq", C.c_char_p), ("end_adapter_seq", C.c_char_p),
+                ("start_adapter_rate", C.c_double), ("start_adapter_amount", C.c_double),
+                ("end_adapter_rate", C.c_double), ("end_adapter_amount", C.c_double),
+                ("junk_reads", C.c_double), ("random_reads", C.c_double), ("chimera", C.c_double),
+                ("glitch_rate", C.c_double), ("glitch_size", C.c_double), ("glitch_skip", C.c_double),
+                ("small_plasmid_bias", C.c_int),
+                ("error_model", C.c_char_p), ("error_model_len", C.c_uint64),
+                ("qscore_model", C.c_char_p), ("qscore_model_len", C.c_uint64)]
+
+
+HOST_EXPORTS = {
+    "rr_sim_default_params": (None, [C.POINTER(rr_sim_params)]),
+    "rr_sim_create": (C.c_int, [C.POINTER(rr_sim_params), C.c_char_p, C.c_uint64, C.POINTER(C.c_void_p)]),
+    "rr_sim_destroy": (None, [C.c_void_p]),
+    "rr_sim_last_error": (C.c_char_p, [C.c_void_p]),
+    "rr_sim_genome_length": (C.c_uint64, [C.c_void_p]),
+    "rr_sim_k": (C.c_uint32, [C.c_void_p]),
+    "rr_quantity_to_bases": (C.c_int64, [C.c_char_p, C.c_uint64]),
+    "rr_sim_attach": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "rr_sim_feed": (C.c_int, [C.c_void_p, C.c_uint64, C.POINTER(C.c_void_p), u64p]),
+    "rr_sim_fastq": (C.c_int, [C.c_void_p, C.POINTER(rr_batch), C.c_uint64, C.POINTER(C.c_void_p), u64p, u64p, u64p]),
+    "rr_sim_item_description": (C.c_int, [C.c_void_p, C.c_uint64, C.c_char_p, C.c_uint64]),
+    "rr_sim_n_refs": (C.c_uint64, [C.c_void_p]),
+    "rr_sim_ref": (C.c_void_p, [C.c_void_p, C.c_uint64, u64p, C.POINTER(C.c_int), f64p, C.POINTER(C.c_char_p)]),
+    "rr_sim_rng_words": (C.c_uint64, [C.c_void_p]),
+}
+EXPORTS.update(HOST_EXPORTS)
+
+
+class Simulation:
+    """Mirror of the reference's `simulate::simulate` orchestrator (src/simulate/mod.rs:27-217):
+    builds main_rng, the models and the references in the reference's order, then feeds batches of
+    work items and formats FASTQ records.  Flags are the CLI's (src/cli/simulate.rs:162-239)."""
+
+    def __init__(self, fasta, seed=42, length=(15000, 13000), identity=(85, 95, 5),
+                 start_adapter=(90, 60), end_adapter=(50, 20),
+                 start_adapter_seq="AATGTACTTCGTTCAGTTACGTATTGCT", end_adapter_seq="GCAATACGTAACTGAACGAAGT",
+                 junk_reads=1, random_reads=1, chimera=1, glitches=(10000, 25, 25), small_plasmid_bias=False,
+                 error_model="random", qscore_model="random", lib=None):
+        self.lib = lib or load_library()
+        if isinstance(fasta, str):
+            fasta = fasta.encode()
+        p = rr_sim_params()
+        self.lib.dll.rr_sim_default_params(C.byref(p))
+        p.seed = seed
+        p.length_mean, p.length_stdev = length
+        p.identity_mean, p.identity_max, p.identity_stdev = identity
+        self._keep = [start_adapter_seq.encode(), end_adapter_seq.encode()]
+        p.start_adapter_seq, p.end_adapter_seq = self._keep
+        p.start_adapter_rate, p.start_adapter_amount = start_adapter
+        p.end_adapter_rate, p.end_adapter_amount = end_adapter
+        p.junk_reads, p.random_reads, p.chimera = junk_reads, random_reads, chimera
+        p.glitch_rate, p.glitch_size, p.glitch_skip = glitches
+        p.small_plasmid_bias = int(small_plasmid_bias)
+        em = None if error_model in (None, "random") else (error_model.encode() if isinstance(error_model, str) else error_model)
+        qm = (qscore_model.encode() if isinstance(qscore_model, str) else qscore_model)
+        self._keep += [em, qm]
+        p.error_model, p.error_model_len = em, (len(em) if em else 0)
+        p.qscore_model, p.qscore_model_len = qm, len(qm)
+        h = C.c_void_p()
+        rc = self.lib.dll.rr_sim_create(C.byref(p), fasta, len(fasta), C.byref(h))
+        if rc:
+            raise RRError(rc, self.lib.dll.rr_sim_last_error(None).decode())
+        self.h = h
+        self.k = int(self.lib.dll.rr_sim_k(h))
+        self.genome_length = int(self.lib.dll.rr_sim_genome_length(h))
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.dll.rr_sim_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _ck(self, rc):
+        if rc:
+            raise RRError(rc, self.lib.dll.rr_sim_last_error(self.h).decode())
+
+    def quantity(self, text):
+        v = self.lib.dll.rr_quantity_to_bases(text.encode(), self.genome_length)
+        if v < 0:
+            raise RRError(2, "cannot parse quantity %r" % text)
+        return int(v)
+
+    def attach(self, ctx):
+        self._ck(self.lib.dll.rr_sim_attach(self.h, ctx.h))
+        ctx.k = self.k
+
+    def feed(self, base_loop):
+        """One batch of the Fragments iterator; returns a numpy array of DESC_DTYPE (a copy)."""
+        p, n = C.c_void_p(), C.c_uint64()
+        self._ck(self.lib.dll.rr_sim_feed(self.h, base_loop, C.byref(p), C.byref(n)))
+        if n.value == 0:
+            return np.zeros(0, dtype=DESC_DTYPE)
+        buf = (C.c_uint8 * (n.value * DESC_DTYPE.itemsize)).from_address(p.value)
+        return np.frombuffer(buf, dtype=DESC_DTYPE).copy()
+
+    def fastq(self, batch_struct, first=0):
+        """FASTQ text for a device batch (rr_batch struct) holding items [first, first+n) of the last feed."""
+        t, n, recs, bases = C.c_void_p(), C.c_uint64(), C.c_uint64(), C.c_uint64()
+        self._ck(self.lib.dll.rr_sim_fastq(self.h, C.byref(batch_struct), first, C.byref(t), C.byref(n), C.byref(recs), C.byref(bases)))
+        return C.string_at(t.value, n.value), recs.value, bases.value
+
+    def refs(self):
+        out = []
+        for i in range(self.lib.dll.rr_sim_n_refs(self.h)):
+            ln, circ, w, rid = C.c_uint64(), C.c_int(), C.c_double(), C.c_char_p()
+            p = self.lib.dll.rr_sim_ref(self.h, i, C.byref(ln), C.byref(circ), C.byref(w), C.byref(rid))
+            out.append(dict(id=rid.value.decode("utf-8", "surrogateescape"), seq=C.string_at(p, ln.value), circular=bool(circ.value), weight=w.value))
+        return out
+
+    def rng_words(self):
+        return int(self.lib.dll.rr_sim_rng_words(self.h))
+
+
+def batch_struct_from_arrays(offsets, lengths, seq, qual, real_identity, k):
+    """Build an rr_batch over caller-owned numpy arrays (keeps references alive on the struct)."""
+    b = rr_batch()
+    keep = [np.ascontiguousarray(offsets, np.uint64), np.ascontiguousarray(lengths, np.uint64), np.ascontiguousarray(seq, np.uint8),
+            np.ascontiguousarray(qual, np.uint8), np.ascontiguousarray(real_identity, np.float64)]
+    b.n_reads = len(keep[1])
+    b.offsets = keep[0].ctypes.data_as(u64p)
+    b.lengths = keep[1].ctypes.data_as(u64p)
+    b.seq = keep[2].ctypes.data_as(u8p)
+    b.qual = keep[3].ctypes.data_as(u8p)
+    b.real_identity = keep[4].ctypes.data_as(f64p)
+    b.total_bytes = int(keep[0][-1]) if len(keep[0]) else 0
+    b.total_bases = int(sum(int(x) - 2 * k for x in keep[1] if x > 14))
+    b.k = k
+    b._keep = keep
+    return b

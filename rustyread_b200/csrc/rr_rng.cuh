@@ -232,7 +232,7 @@ RR_HD double beta_sample(const BetaParams& B, R& rng) {
     }
   }
   if (!B.switched) {
-    if (isinf(w)) return 1.0;
+    if (w > 1.7976931348623157e308) return 1.0;  // w == +inf
     return w / (B.b + w);
   }
   return B.b / (B.b + w);

@@ -1,0 +1,210 @@
+"""CPU tests of the product's host side (feeder, loaders, reference ingest, FASTQ writer) against the oracle,
+and of the C-ABI surface.  No compute entry point is called here (there is no GPU on this box)."""
+import ctypes as C
+import os
+import random
+import re
+
+import numpy as np
+import pytest
+
+import helpers
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def rr():
+    import rustyread_b200
+
+    rustyread_b200.build_library()
+    return rustyread_b200
+
+
+def test_library_exports_every_declared_symbol(rr):
+    lib = rr.load_library()
+    declared = set()
+    for h in ("rustyread_b200.h", "rustyread_b200_host.h"):
+        text = open(os.path.join(ROOT, "include", h)).read()
+        text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+        declared |= set(re.findall(r"\b(rr_[a-z0-9_]+)\s*\(", text))
+    assert len(declared) >= 30
+    for name in sorted(declared):
+        assert hasattr(lib.dll, name), name
+    import rustyread_b200.capi as capi
+
+    assert declared == set(capi.EXPORTS), declared ^ set(capi.EXPORTS)
+
+
+def test_no_cpu_fallback(rr):
+    lib = rr.load_library()
+    if lib.device_count() > 0:
+        pytest.skip("a GPU is present")
+    with pytest.raises(rr.RRError) as e:
+        rr.Context(0)
+    assert "no CPU fallback" in str(e.value)
+
+
+def test_desc_struct_layout(rr):
+    import rustyread_b200.capi as capi
+
+    assert capi.DESC_DTYPE.itemsize == 80
+    assert capi.DESC_DTYPE.fields["start"][1] == 32 and capi.DESC_DTYPE.fields["seed"][1] == 72
+
+
+def test_quantity(rr):  # src/cli/simulate.rs:247-290
+    q = lambda s, g=1000: rr.load_library().dll.rr_quantity_to_bases(s.encode(), g)
+    assert (q("50"), q("50K"), q("50M"), q("50G"), q("50x")) == (50, 50_000, 50_000_000, 50_000_000_000, 50_000)
+    assert q("bépo") == -1 and q("50k") == -1 and q("x") == -1 and q("") == -1 and q("1.5x") == -1
+
+
+SPECS = {
+    "default": ({}, [300_000], set(), 3_000_000),
+    "cfg4": (dict(length=(50000.0, 40000.0), identity=(75.0, 90.0, 8.0), glitch=(2000.0, 50.0, 50.0), rates=(1.0, 1.0, 5.0)), [500_000], set(), 5_000_000),
+    "plasmids_bias": (dict(rates=(10.0, 10.0, 1.0), small_plasmid_bias=True, length=(6000.0, 5000.0)), None, None, 2_000_000),
+    "plasmids_nobias": (dict(rates=(10.0, 10.0, 20.0), small_plasmid_bias=False, length=(6000.0, 5000.0)), None, None, 2_000_000),
+    "fixed": (dict(length=(5000.0, 0.0), identity=(90.0, 90.0, 5.0), rates=(0.0, 0.0, 0.0)), [100_000, 20_000], {1}, 1_000_000),
+    "small_shape": (dict(length=(3000.0, 6000.0)), [100_000], set(), 1_000_000),  # Gamma shape < 1 (unpinned branch)
+}
+
+
+def _fasta(orc, name):
+    spec, contigs, circ, target = SPECS[name]
+    if contigs is None:
+        rnd = random.Random(5)
+        contigs = [int(2000 * (25 ** rnd.random())) for _ in range(40)]
+        return helpers.random_fasta(orc, contigs, circular=set(range(0, 40, 2)), depth={3: "2.5", 8: "0.5"})
+    return helpers.random_fasta(orc, contigs, circular=circ)
+
+
+def _sim(rr, fasta, s):
+    import rustyread_b200.capi as capi
+
+    a = s["adapter"]
+    return capi.Simulation(fasta, seed=s["seed"], length=s["length"], identity=s["identity"], start_adapter=(a[2], a[3]), end_adapter=(a[4], a[5]),
+                           start_adapter_seq=a[0], end_adapter_seq=a[1], junk_reads=s["rates"][0], random_reads=s["rates"][1], chimera=s["rates"][2],
+                           glitches=s["glitch"], small_plasmid_bias=s["small_plasmid_bias"],
+                           error_model=s["error_model"] or "random", qscore_model=s["qscore_model"])
+
+
+def _oracle_workload(orc, fasta, spec):
+    s = dict(helpers.DEFAULT)
+    s.update(spec)
+    w = orc.workload(s["seed"])
+    w.set_length(*s["length"])
+    w.set_references(fasta, adjusted=True, small_plasmid_bias=s["small_plasmid_bias"])
+    w.set_identity(*s["identity"])
+    w.set_adapter(*s["adapter"])
+    w.set_glitch(*s["glitch"])
+    w.set_error_model(s["error_model"])
+    w.set_qscore_model(s["qscore_model"] if s["qscore_model"] in ("random", "ideal") else "file", None if s["qscore_model"] in ("random", "ideal") else s["qscore_model"])
+    w.set_rates(*s["rates"])
+    return w, s
+
+
+@pytest.mark.parametrize("name", sorted(SPECS))
+def test_feeder_matches_oracle(rr, orc, name):
+    import rustyread_b200.capi as capi
+
+    spec, _, _, target = SPECS[name]
+    fasta = _fasta(orc, name)
+    w, s = _oracle_workload(orc, fasta, spec)
+    sim = _sim(rr, fasta, s)
+    # reference ingest: ids, bytes, circular flags and adjusted weights
+    for a, b in zip(sim.refs(), w.refs()):
+        assert a == b
+    for batch in range(2):  # two consecutive batches share main_rng (--number_base_store semantics)
+        n = w.feed(target)
+        d, ident, _ = w.items()
+        want = capi.descs_from_oracle_items(d, ident)
+        got = sim.feed(target)
+        assert len(got) == n
+        for f in capi.DESC_DTYPE.names:
+            if f in ("reserved",):
+                continue
+            assert np.array_equal(got[f], want[f]), (name, batch, f)
+    assert sim.rng_words() == orc.lib.orc_rng_words(w.rng_handle())
+
+
+def test_feeder_with_file_error_model_draws(rr, orc, goldens):
+    # Error::from_stream consumes main_rng (src/model/error.rs:65-69) before the first fragment is drawn
+    import rustyread_b200.capi as capi
+
+    fasta = helpers.random_fasta(orc, [50_000])
+    spec = dict(error_model=goldens["model.error.MODEL"], qscore_model=goldens["model.quality.MODEL"], length=(3000.0, 2500.0))
+    w, s = _oracle_workload(orc, fasta, spec)
+    sim = _sim(rr, fasta, s)
+    assert sim.k == 7
+    n = w.feed(500_000)
+    d, ident, _ = w.items()
+    got = sim.feed(500_000)
+    want = capi.descs_from_oracle_items(d, ident)
+    assert np.array_equal(got["seed"], want["seed"]) and np.array_equal(got["identity"], want["identity"])
+
+
+def _batch_from_oracle(w, k):
+    import rustyread_b200.capi as capi
+
+    seq, so = w.out("seq")
+    qual, _ = w.out("qual")
+    lens = (so[1:] - so[:-1]).astype(np.uint64)
+    return capi.batch_struct_from_arrays(so, lens, seq, qual, w.out_identity(), k)
+
+
+@pytest.mark.parametrize("store", ["", "150K"])
+def test_fastq_writer_matches_oracle_simulate(rr, orc, store):
+    # whole-run text: names (UUIDv3 of main_rng draws), descriptions, trimming, the len <= 14 filter, batching
+    fasta = helpers.random_fasta(orc, [60_000, 4_000], circular={1})
+    params = dict(seed=7, length="2000,1800", identity="85,95,5", quantity="8x", junk_reads=5, random_reads=5, chimera=10,
+                  glitches="1000,25,25", threads=4)
+    if store:
+        params["number_base_store"] = store
+    text, stats = orc.simulate(params, fasta, capture=True)
+    spec = dict(seed=7, length=(2000.0, 1800.0), rates=(5.0, 5.0, 10.0), glitch=(1000.0, 25.0, 25.0))
+    w, s = _oracle_workload(orc, fasta, spec)
+    sim = _sim(rr, fasta, s)
+    total = sim.quantity("8x")
+    limit = sim.quantity(store) if store else total
+    produced, out, recs, bases = 0, b"", 0, 0
+    while produced < total:  # the batch loop of src/simulate/mod.rs:153-214
+        base_loop = min(limit, total - produced)
+        produced += base_loop
+        descs = sim.feed(base_loop)
+        n = w.feed(base_loop)
+        assert n == len(descs)
+        w.generate(threads=4, keep_cigar_raw=False)
+        # the oracle workload's main rng must follow the writer's u128 draws too: replay them
+        half = len(descs) // 2
+        b = _batch_from_oracle(w, 7)
+        # exercise sharded formatting: two shards in order
+        import rustyread_b200.capi as capi
+
+        seq, so = w.out("seq")
+        qual, _ = w.out("qual")
+        ident = w.out_identity()
+        lens = (so[1:] - so[:-1]).astype(np.uint64)
+        for lo, hi in ((0, half), (half, len(descs))):
+            sb = capi.batch_struct_from_arrays(so[lo:hi + 1] - so[lo], lens[lo:hi], seq[int(so[lo]):int(so[hi])] if hi > lo else seq[:1], qual[int(so[lo]):int(so[hi])] if hi > lo else qual[:1], ident[lo:hi], 7)
+            t, r, bs = sim.fastq(sb, first=lo)
+            out += t
+            recs += r
+            bases += bs
+            for _ in range(r):  # keep the oracle-side main rng in step (2 u64 per emitted read)
+                orc.lib.orc_rng_next_u64(w.rng_handle())
+                orc.lib.orc_rng_next_u64(w.rng_handle())
+    assert recs == stats["reads"] and bases == stats["bases"]
+    assert out.decode() == text
+
+
+def test_loader_rejects_what_the_reference_rejects(rr, orc):
+    import rustyread_b200.capi as capi
+
+    fasta = helpers.random_fasta(orc, [10_000])
+    with pytest.raises(rr.RRError):
+        capi.Simulation(fasta, length=(0, 0))
+    with pytest.raises(rr.RRError):
+        capi.Simulation(fasta, identity=(0, 0, 0))
+    with pytest.raises(rr.RRError):
+        capi.Simulation(b"")
+    with pytest.raises(rr.RRError):
+        capi.Simulation(fasta, qscore_model="overall;3;1:0.5,\n=;1;x:0.5,\n")
