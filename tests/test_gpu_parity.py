@@ -331,3 +331,29 @@ def test_invalid_inputs_fail_loudly(rr, orc):
     with pytest.raises(rr.RRError):
         ctx.set_qscore_model(1, [(b"=", [1], [1.0])])  # missing X / I
     ctx.close()
+
+
+def test_whole_simulate_fastq_is_byte_identical(orc):
+    """Product path end to end (host feeder -> kernels -> FASTQ writer) vs the oracle's simulate():
+    every byte of the FASTQ text, including read names and descriptions, over two --number_base_store batches."""
+    import rustyread_b200.capi as capi
+
+    fasta = helpers.random_fasta(orc, [80_000, 6_000, 900], circular={1, 2})
+    params = dict(seed=11, length="2500,2200", identity="80,97,8", quantity="12x", junk_reads=4, random_reads=4, chimera=10,
+                  glitches="800,25,25", threads=8, number_base_store="600K")
+    text, stats = orc.simulate(params, fasta, capture=True)
+    sim = capi.Simulation(fasta, seed=11, length=(2500, 2200), identity=(80, 97, 8), junk_reads=4, random_reads=4, chimera=10, glitches=(800, 25, 25))
+    ctx = capi.Context(0)
+    sim.attach(ctx)
+    total, limit = sim.quantity("12x"), sim.quantity("600K")
+    produced, out, recs = 0, b"", 0
+    while produced < total:
+        base_loop = min(limit, total - produced)
+        produced += base_loop
+        batch = ctx.generate(sim.feed(base_loop))
+        t, r, _ = sim.fastq(batch.struct, 0)
+        out += t
+        recs += r
+    assert recs == stats["reads"]
+    assert out.decode() == text
+    ctx.close()
