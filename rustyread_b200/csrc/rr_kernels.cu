@@ -629,8 +629,8 @@ RR_API int rr_generate(rr_ctx* ctx, uint64_t n, const rr_desc* descs, rr_batch* 
 __global__ void rr_debug_align_kernel(ReadKernelParams P, const uint8_t* q, uint32_t m, const uint8_t* t, uint32_t n, uint8_t* cigar,
                                       uint32_t* out) {
   __shared__ WarpSmem ws;
-  AlignOut a = warp_align(&ws, P, 0, q, m, t, n, cigar, (uint64_t)m + n, threadIdx.x & 31);
-  if (threadIdx.x == 0) { out[0] = a.n_ops; out[1] = a.edits; out[2] = (uint32_t)a.status; }
+  uint64_t a = warp_align(&ws, P, 0, q, m, t, n, cigar, (uint64_t)m + n, threadIdx.x & 31);
+  if (threadIdx.x == 0) { out[0] = align_nops(a); out[1] = align_edits(a); out[2] = align_status(a); }
 }
 
 RR_API int rr_debug_align(rr_ctx* ctx, const uint8_t* query, uint32_t m, const uint8_t* target, uint32_t n, uint8_t* cigar,
@@ -664,7 +664,7 @@ RR_API int rr_debug_align(rr_ctx* ctx, const uint8_t* query, uint32_t m, const u
 }
 
 __global__ void rr_debug_rng_kernel(uint64_t seed, uint64_t first, uint32_t n, uint32_t* out) {
-  __shared__ uint32_t words[RNG_WORDS];
+  __shared__ uint32_t words[RNG_WORDS + 8];
   WarpRng rng;
   rng.seed(seed, words, threadIdx.x & 31);
   rng.cur = first;

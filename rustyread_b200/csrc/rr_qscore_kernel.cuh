@@ -114,7 +114,7 @@ __global__ void __launch_bounds__(Q_THREADS) rr_qscore_kernel(const __grid_const
           uint32_t out[16];
           chacha12_block(key, b_first + (uint64_t)tid, out);
 #pragma unroll
-          for (int j = 0; j < 16; ++j) s_words[WarpRng::swz((uint32_t)tid * 16u + j)] = out[j];
+          for (int j = 0; j < 16; ++j) s_words[rng_swz((uint32_t)tid * 16u + j)] = out[j];
         }
       }
       __syncthreads();
@@ -138,7 +138,7 @@ __global__ void __launch_bounds__(Q_THREADS) rr_qscore_kernel(const __grid_const
           P.status[ridx] = ST_QUAL;
         } else {
           const uint32_t woff = (uint32_t)(w_first + 2 * (uint64_t)r - (b_first << 4));
-          const uint64_t v = (uint64_t)s_words[WarpRng::swz(woff)] | ((uint64_t)s_words[WarpRng::swz(woff + 1)] << 32);
+          const uint64_t v = (uint64_t)s_words[rng_swz(woff)] | ((uint64_t)s_words[rng_swz(woff + 1)] << 32);
           const uint32_t d0 = Q.dist_off[dist], nd = Q.dist_off[dist + 1] - d0;
           const double chosen = u64_to_unit12(v) * Q.scale[dist] + 0.0;
           uint32_t lo = 0, hi = nd - 1;  // partition_point over the first nd - 1 partial sums

@@ -5,6 +5,12 @@
 
 namespace rr {
 
+// What an out-of-line stage hands back: the generator state (kept in registers by the caller) + one value.
+struct StageOut {
+  uint64_t base, cur, value;
+  uint32_t status;
+};
+
 __device__ __forceinline__ uint8_t complement(uint8_t c) {
   // bio::alphabets::dna::complement (IUPAC aware, case preserving); used by Reference::new (src/references.rs:27)
   switch (c) {
@@ -20,7 +26,7 @@ __device__ __forceinline__ uint8_t complement(uint8_t c) {
 
 // Adapter::get_start / get_end (src/model/adapter.rs:64-93): Bernoulli(rate), then a Beta-distributed
 // prefix of the adapter.  Returns the number of bytes appended.
-__device__ uint32_t add_adapter(WarpRng& rng, const DeviceModels& M, bool end_side, uint8_t* dst, int lane) {
+__device__ __forceinline__ uint32_t add_adapter(WarpRng& rng, const DeviceModels& M, bool end_side, uint8_t* dst, int lane) {
   double rate = end_side ? M.end_rate : M.start_rate;
   int has = end_side ? M.has_end : M.has_start;
   if (!rng.gen_bool(rate) || !has) return 0;
@@ -34,8 +40,8 @@ __device__ uint32_t add_adapter(WarpRng& rng, const DeviceModels& M, bool end_si
 }
 
 // add_fragment (src/simulate/mod.rs:295-339).  `tmp` = 8 bytes of shared memory.
-__device__ uint64_t add_fragment(WarpRng& rng, const DeviceModels& M, uint32_t type, uint32_t ref_idx, uint32_t strand,
-                                 uint64_t start, uint64_t end, uint8_t* dst, uint8_t* tmp, int lane) {
+__device__ __forceinline__ uint64_t add_fragment(WarpRng& rng, const DeviceModels& M, uint32_t type, uint32_t ref_idx, uint32_t strand,
+                                                 uint64_t start, uint64_t end, uint8_t* dst, uint8_t* tmp, int lane) {
   if (type == RR_JUNK) {  // mod.rs:310-317
     uint64_t unit = rng.gen_range_u64(1, 5);
     __syncwarp();
@@ -68,181 +74,12 @@ __device__ uint64_t add_fragment(WarpRng& rng, const DeviceModels& M, uint32_t t
   return n1 + n2;
 }
 
-// State of `changes.last()` plus the streamed stitch of sequence() (src/simulate/error.rs:219-246).
-// A Change only ever grows by appending to seq / cigar (merge, error.rs:105-152), and only the last
-// one can change, so err / CIGAR are written once, in order, as the walk proceeds.
-struct Stitch {
-  const uint8_t* raw;
-  uint64_t L;
-  uint8_t* err;
-  uint8_t* cig;
-  uint64_t cap;
-  uint64_t err_len, cig_len;
-  uint64_t pos_in_raw;   // sequence(): end of the last emitted change
-  uint64_t real_edit;
-  bool has_last, l_emit;
-  uint64_t lb, le, lseq_len, ledit;
-  int status;
-};
-
-__device__ __forceinline__ void st_finalize_last(Stitch& S) {
-  if (S.has_last && S.l_emit) {
-    S.real_edit += S.ledit;
-    S.pos_in_raw = S.le;
-  }
-}
-
-__device__ __forceinline__ bool st_reserve(Stitch& S, uint64_t n_err, uint64_t n_cig) {
-  if (S.err_len + n_err > S.cap || S.cig_len + n_cig > S.cap) {
-    S.status = ST_OUT_OVERFLOW;
-    return false;
-  }
-  return true;
-}
-
-__device__ void st_emit_gap(Stitch& S, uint64_t upto, int lane) {  // raw[pos_in_raw..upto) copied, '=' in the CIGAR
-  if (upto <= S.pos_in_raw) return;
-  uint64_t n = upto - S.pos_in_raw;
-  if (!st_reserve(S, n, n)) return;
-  const uint8_t* src = S.raw + S.pos_in_raw;
-  uint8_t* de = S.err + S.err_len;
-  uint8_t* dc = S.cig + S.cig_len;
-  for (uint64_t i = lane; i < n; i += 32) {
-    de[i] = src[i];
-    dc[i] = '=';
-  }
-  S.err_len += n;
-  S.cig_len += n;
-}
-
-__device__ void st_emit_seq(Stitch& S, const uint8_t* q, uint64_t n, int lane) {
-  if (!st_reserve(S, n, 0)) return;
-  uint8_t* de = S.err + S.err_len;
-  for (uint64_t i = lane; i < n; i += 32) de[i] = q[i];
-  S.err_len += n;
-}
-
-// AbsChanges::add_change (src/simulate/error.rs:173-193) with contain / overlap / merge /
-// update_align (error.rs:83-164).  Returns the edit count to subtract from the target.
-__device__ uint64_t add_change(Stitch& S, WarpSmem* ws, const ReadKernelParams& P, uint32_t gwarp, uint64_t ob, uint64_t oe,
-                               const uint8_t* oseq, uint64_t olen, int lane) {
-  if (S.has_last) {
-    const uint64_t l_end_err = S.lb + S.lseq_len;
-    const uint64_t o_end_err = ob + olen;
-    if (oe <= l_end_err || oe <= S.le || o_end_err <= l_end_err) return 0;  // contain
-    if (ob < l_end_err || ob < S.le) {                                       // overlap -> merge
-      uint64_t es, old_end = S.le;
-      if (ob < l_end_err) {
-        uint64_t ovl = l_end_err - ob;
-        es = ovl;  // olen > ovl holds because the change is not contained
-        S.le = S.le + oe - ob - ovl;
-      } else {
-        es = 0;
-        S.le = ob + olen;
-      }
-      uint64_t rs, re;
-      if (S.le < S.L - 1) {
-        if (old_end < S.le) { rs = old_end; re = S.le; } else { rs = S.le; re = old_end; }
-      } else { rs = old_end; re = S.L; }
-      if (rs > re || re > S.L || es > olen) { S.status = ST_REF_PANIC; return 0; }
-      uint64_t add = olen - es;
-      S.lseq_len += add;
-      if (S.l_emit) st_emit_seq(S, oseq + es, add, lane);
-      if (S.status) return 0;
-      AlignOut a = warp_align(ws, P, gwarp, oseq + es, (uint32_t)add, S.raw + rs, (uint32_t)(re - rs),
-                              S.l_emit ? S.cig + S.cig_len : nullptr, S.cap - S.cig_len, lane);
-      if (a.status) { S.status = a.status; return 0; }
-      if (S.l_emit) S.cig_len += a.n_ops;
-      S.ledit += a.edits;
-      return a.edits;
-    }
-  }
-  // push a new change (update_align: error.rs:155-164)
-  st_finalize_last(S);
-  uint64_t e = oe > S.L ? S.L : oe;
-  if (ob > e) { S.status = ST_REF_PANIC; return 0; }
-  bool emit = ob >= S.pos_in_raw;  // sequence(): `if change.begin() < pos_in_raw { continue }`
-  if (emit) {
-    st_emit_gap(S, ob, lane);
-    st_emit_seq(S, oseq, olen, lane);
-    if (S.status) return 0;
-  }
-  AlignOut a = warp_align(ws, P, gwarp, oseq, (uint32_t)olen, S.raw + ob, (uint32_t)(e - ob),
-                          emit ? S.cig + S.cig_len : nullptr, S.cap - S.cig_len, lane);
-  if (a.status) { S.status = a.status; return 0; }
-  if (emit) S.cig_len += a.n_ops;
-  S.has_last = true;
-  S.l_emit = emit;
-  S.lb = ob;
-  S.le = oe;
-  S.lseq_len = olen;
-  S.ledit = a.edits;
-  return a.edits;
-}
-
-// Error::add_errors_to_kmer (src/model/error.rs:93-107) / random_error (error.rs:116-135).
-// Writes the altered k-mer to ws->alt, returns its length.
-__device__ uint32_t make_alt(WarpRng& rng, const DeviceModels& M, WarpSmem* ws, const uint8_t* kmer, int lane) {
-  const uint32_t k = M.k;
-  __syncwarp();
-  if (M.em_index) {
-    // 2-bit code of the k-mer; any byte outside ACGT misses the table
-    uint32_t part = 0, bad = 0;
-    if ((uint32_t)lane < k) {
-      uint8_t c = kmer[lane];
-      uint32_t s = c == 'A' ? 0u : c == 'C' ? 1u : c == 'G' ? 2u : c == 'T' ? 3u : 4u;
-      bad = s > 3u;
-      part = (s & 3u) << (2 * (k - 1 - lane));
-    }
-    uint32_t code = __reduce_or_sync(0xffffffffu, part);
-    bool anybad = __any_sync(0xffffffffu, bad);
-    int key = anybad ? -1 : M.em_index[code];
-    if (key >= 0) {
-      uint32_t a0 = M.em_alt_begin[key], a1 = M.em_alt_begin[key + 1];
-      uint32_t na = a1 - a0;
-      double chosen = u64_to_unit12(rng.next_u64()) * M.em_scale[key] + 0.0;
-      // WeightedIndex: number of partial sums <= chosen among the first na - 1
-      uint32_t idx = 0;
-      for (uint32_t b = 0; b + 1 < na; b += 32) {
-        uint32_t i = b + lane;
-        bool le = (i + 1 < na) && (M.em_cum[a0 + i] <= chosen);
-        idx += __popc(__ballot_sync(0xffffffffu, le));
-      }
-      uint32_t o0 = M.em_alt_off[a0 + idx], o1 = M.em_alt_off[a0 + idx + 1];
-      uint32_t n = o1 - o0;
-      for (uint32_t i = lane; i < n; i += 32) ws->alt[i] = M.em_alt_bytes[o0 + i];
-      __syncwarp();
-      return n;
-    }
-  }
-  uint32_t ep = (uint32_t)rng.gen_range_u64(0, k - 1);
-  uint32_t kind = rng.gen_range_u32(1, 3);  // 1 substitution, 2 insertion, 3 deletion
-  uint8_t at = kmer[ep];
-  uint8_t nb = 0;
-  if (kind == 1) nb = rng.random_base_diff(at);
-  else if (kind == 2) nb = rng.random_base();
-  uint32_t n = kind == 1 ? k : (kind == 2 ? k + 1 : k - 1);
-  if ((uint32_t)lane < n) {
-    uint32_t i = lane;
-    uint8_t c;
-    if (kind == 1) c = (i == ep) ? nb : kmer[i];
-    else if (kind == 2) c = (i < ep) ? kmer[i] : (i == ep ? nb : kmer[i - 1]);
-    else c = (i < ep) ? kmer[i] : kmer[i + 1];
-    ws->alt[i] = c;
-  }
-  __syncwarp();
-  return n;
-}
-
-__device__ void process_read(const ReadKernelParams& P, WarpSmem* ws, uint32_t gwarp, uint32_t ridx, int lane) {
+// ---- K2 (out of line): the raw fragment of generate_read, src/simulate/mod.rs:243-271.  value = raw length ----
+__device__ __noinline__ StageOut stage_assemble(WarpRng rng, const ReadKernelParams& P, WarpSmem* ws, uint32_t ridx, uint8_t* raw) {
   const DeviceModels& M = P.M;
+  const int lane = rng.lane;
   const rr_desc d = P.descs[ridx];
   const uint32_t k = M.k;
-  WarpRng rng;
-  rng.seed(d.seed, ws->rng, lane);
-
-  // ---- K2: raw fragment (src/simulate/mod.rs:243-271) ----
-  uint8_t* raw = P.raw + P.raw_off[ridx];
   uint64_t L = 0;
   rng.random_seq(k, raw);
   L += k;
@@ -257,6 +94,189 @@ __device__ void process_read(const ReadKernelParams& P, WarpSmem* ws, uint32_t g
   rng.random_seq(k, raw + L);
   L += k;
   __syncwarp();
+  StageOut o;
+  o.base = rng.base;
+  o.cur = rng.cur;
+  o.value = L;
+  o.status = ST_OK;
+  return o;
+}
+
+// ---- add_glitches (out of line), src/simulate/error.rs:250-264: positions, skips and inserted bases are drawn up front.
+// value = number of glitches recorded in the warp's scratch ----
+__device__ __noinline__ StageOut stage_glitches(WarpRng rng, const ReadKernelParams& P, uint32_t gwarp, uint64_t L) {
+  const DeviceModels& M = P.M;
+  const int lane = rng.lane;
+  GlitchRec* grec = P.sc_grec + (uint64_t)gwarp * P.sc_grec_cap;
+  uint8_t* gseq = P.sc_gseq + (uint64_t)gwarp * P.sc_gseq_cap;
+  uint32_t ng = 0, status = ST_OK;
+  uint64_t position = 0, gbytes = 0;
+  for (;;) {
+    uint64_t begin = geometric_sample(M.g_dist, rng);
+    uint64_t end = begin + geometric_sample(M.g_skip, rng);
+    uint64_t size = geometric_sample(M.g_size, rng);
+    if (gbytes + size > P.sc_gseq_cap || ng >= P.sc_grec_cap) { status = ST_GLITCH_OVERFLOW; break; }
+    __syncwarp();
+    rng.random_seq(size, gseq + gbytes);
+    position += begin;
+    if (position > L || position + end > L) break;
+    if (lane == 0) {
+      GlitchRec g;
+      g.begin = position;
+      g.end = position + (end - begin);
+      g.seq_off = (uint32_t)gbytes;
+      g.seq_len = (uint32_t)size;
+      grec[ng] = g;
+    }
+    ++ng;
+    gbytes += size;
+  }
+  __syncwarp();
+  StageOut o;
+  o.base = rng.base;
+  o.cur = rng.cur;
+  o.value = ng;
+  o.status = status;
+  return o;
+}
+
+// Error::add_errors_to_kmer on a k-mer that is in the table (src/model/error.rs:96-100): one WeightedIndex draw.
+// Out of line: only file models reach it.  value = alternative length (bytes in ws->alt).
+__device__ __noinline__ StageOut stage_alt_from_table(WarpRng rng, const DeviceModels& M, WarpSmem* ws, int key) {
+  const int lane = rng.lane;
+  uint32_t a0 = M.em_alt_begin[key], a1 = M.em_alt_begin[key + 1];
+  uint32_t na = a1 - a0;
+  double chosen = u64_to_unit12(rng.next_u64()) * M.em_scale[key] + 0.0;
+  uint32_t idx = 0;  // number of partial sums <= chosen among the first na - 1
+  for (uint32_t b = 0; b + 1 < na; b += 32) {
+    uint32_t i = b + lane;
+    bool le = (i + 1 < na) && (M.em_cum[a0 + i] <= chosen);
+    idx += __popc(__ballot_sync(0xffffffffu, le));
+  }
+  uint32_t o0 = M.em_alt_off[a0 + idx], o1 = M.em_alt_off[a0 + idx + 1];
+  uint32_t n = o1 - o0;
+  __syncwarp();
+  for (uint32_t i = lane; i < n; i += 32) ws->alt[i] = M.em_alt_bytes[o0 + i];
+  __syncwarp();
+  StageOut o;
+  o.base = rng.base;
+  o.cur = rng.cur;
+  o.value = n;
+  o.status = ST_OK;
+  return o;
+}
+
+// State of `changes.last()` plus the streamed stitch of sequence() (src/simulate/error.rs:219-246).
+// A Change only ever grows by appending to seq / cigar (merge, error.rs:105-152), and only the last
+// one can change, so err / CIGAR are written once, in order, as the walk proceeds.
+struct Stitch {
+  const uint8_t* raw;
+  uint64_t L;
+  uint8_t* err;
+  uint8_t* cig;
+  uint64_t cap;
+  uint64_t err_len, cig_len;
+  uint64_t pos_in_raw;   // sequence(): end of the last emitted change
+  uint64_t real_edit;
+  bool has_last, l_emit;
+  uint64_t lb, le, lseq_len, ledit;
+  uint32_t status;
+};
+
+__device__ __forceinline__ bool st_reserve(Stitch& S, uint64_t n_err, uint64_t n_cig) {
+  if (S.err_len + n_err > S.cap || S.cig_len + n_cig > S.cap) {
+    S.status = ST_OUT_OVERFLOW;
+    return false;
+  }
+  return true;
+}
+
+__device__ __forceinline__ void st_emit_gap(Stitch& S, uint64_t upto, int lane) {  // raw[pos_in_raw..upto) copied, '=' in the CIGAR
+  if (upto <= S.pos_in_raw) return;
+  uint64_t n = upto - S.pos_in_raw;
+  if (!st_reserve(S, n, n)) return;
+  const uint8_t* src = S.raw + S.pos_in_raw;
+  uint8_t* de = S.err + S.err_len;
+  uint8_t* dc = S.cig + S.cig_len;
+  for (uint64_t i = lane; i < n; i += 32) {
+    de[i] = src[i];
+    dc[i] = '=';
+  }
+  S.err_len += n;
+  S.cig_len += n;
+}
+
+__device__ __forceinline__ void st_emit_seq(Stitch& S, const uint8_t* q, uint64_t n, int lane) {
+  if (!st_reserve(S, n, 0)) return;
+  uint8_t* de = S.err + S.err_len;
+  for (uint64_t i = lane; i < n; i += 32) de[i] = q[i];
+  S.err_len += n;
+}
+
+// AbsChanges::add_change (src/simulate/error.rs:173-193) with contain / overlap / merge /
+// update_align (error.rs:83-164).  Returns the edit count to subtract from the target.
+// One alignment call site: the merge and the push cases only differ in which slices are aligned.
+__device__ __forceinline__ uint64_t add_change(Stitch& S, WarpSmem* ws, const ReadKernelParams& P, uint32_t gwarp, uint64_t ob, uint64_t oe,
+                                               const uint8_t* oseq, uint64_t olen, int lane) {
+  bool merge = false;
+  uint64_t es = 0, rs, re;
+  if (S.has_last) {
+    const uint64_t l_end_err = S.lb + S.lseq_len;
+    if (oe <= l_end_err || oe <= S.le || ob + olen <= l_end_err) return 0;  // contain (error.rs:83-88)
+    if (ob < l_end_err || ob < S.le) {                                       // overlap -> merge (error.rs:105-152)
+      merge = true;
+      const uint64_t old_end = S.le;
+      if (ob < l_end_err) {
+        es = l_end_err - ob;  // olen > es holds because the change is not contained
+        S.le = S.le + oe - ob - es;
+      } else {
+        S.le = ob + olen;
+      }
+      if (S.le < S.L - 1) {
+        if (old_end < S.le) { rs = old_end; re = S.le; } else { rs = S.le; re = old_end; }
+      } else { rs = old_end; re = S.L; }
+      if (rs > re || re > S.L || es > olen) { S.status = ST_REF_PANIC; return 0; }
+      S.lseq_len += olen - es;
+    }
+  }
+  if (!merge) {  // push a new change (update_align: error.rs:155-164)
+    if (S.has_last && S.l_emit) {  // the previous change is final: sequence() accounts for it
+      S.real_edit += S.ledit;
+      S.pos_in_raw = S.le;
+    }
+    rs = ob;
+    re = oe > S.L ? S.L : oe;
+    if (rs > re) { S.status = ST_REF_PANIC; return 0; }
+    S.has_last = true;
+    S.l_emit = ob >= S.pos_in_raw;  // sequence(): `if change.begin() < pos_in_raw { continue }`
+    S.lb = ob;
+    S.le = oe;
+    S.lseq_len = olen;
+    S.ledit = 0;
+    if (S.l_emit) st_emit_gap(S, ob, lane);
+  }
+  const uint64_t add = olen - es;
+  if (S.l_emit) st_emit_seq(S, oseq + es, add, lane);
+  if (S.status) return 0;
+  const uint64_t a = warp_align(ws, P, gwarp, oseq + es, (uint32_t)add, S.raw + rs, (uint32_t)(re - rs),
+                                S.l_emit ? S.cig + S.cig_len : nullptr, S.cap - S.cig_len, lane);
+  if (align_status(a)) { S.status = align_status(a); return 0; }
+  if (S.l_emit) S.cig_len += align_nops(a);
+  S.ledit += align_edits(a);
+  return align_edits(a);
+}
+
+__device__ __forceinline__ void process_read(const ReadKernelParams& P, WarpSmem* ws, uint32_t gwarp, uint32_t ridx, int lane) {
+  const DeviceModels& M = P.M;
+  const uint32_t k = M.k;
+  WarpRng rng;
+  rng.seed(P.descs[ridx].seed, ws->rng, lane);
+
+  uint8_t* raw = P.raw + P.raw_off[ridx];
+  StageOut so = stage_assemble(rng, P, ws, ridx, raw);
+  rng.base = so.base;
+  rng.cur = so.cur;
+  const uint64_t L = so.value;
 
   Stitch S;
   S.raw = raw;
@@ -273,35 +293,16 @@ __device__ void process_read(const ReadKernelParams& P, WarpSmem* ws, uint32_t g
   S.status = ST_OK;
 
   // ---- K3: error::sequence (src/simulate/error.rs:201-217) ----
-  double target = (1.0 - d.identity) * (double)L;  // number_of_edit, error.rs:196-198
-
-  // add_glitches (error.rs:250-264): positions, skips and inserted bases are drawn up front
-  GlitchRec* grec = P.sc_grec + (uint64_t)gwarp * P.sc_grec_cap;
-  uint8_t* gseq = P.sc_gseq + (uint64_t)gwarp * P.sc_gseq_cap;
+  double target = (1.0 - P.descs[ridx].identity) * (double)L;  // number_of_edit, error.rs:196-198
+  const GlitchRec* grec = P.sc_grec + (uint64_t)gwarp * P.sc_grec_cap;
+  const uint8_t* gseq = P.sc_gseq + (uint64_t)gwarp * P.sc_gseq_cap;
   uint32_t ng = 0;
   if (M.has_distance) {
-    uint64_t position = 0, gbytes = 0;
-    for (;;) {
-      uint64_t begin = geometric_sample(M.g_dist, rng);
-      uint64_t end = begin + geometric_sample(M.g_skip, rng);
-      uint64_t size = geometric_sample(M.g_size, rng);
-      if (gbytes + size > P.sc_gseq_cap || ng >= P.sc_grec_cap) { S.status = ST_GLITCH_OVERFLOW; break; }
-      __syncwarp();
-      rng.random_seq(size, gseq + gbytes);
-      position += begin;
-      if (position > L || position + end > L) break;
-      if (lane == 0) {
-        GlitchRec g;
-        g.begin = position;
-        g.end = position + (end - begin);
-        g.seq_off = (uint32_t)gbytes;
-        g.seq_len = (uint32_t)size;
-        grec[ng] = g;
-      }
-      ++ng;
-      gbytes += size;
-    }
-    __syncwarp();
+    so = stage_glitches(rng, P, gwarp, L);
+    rng.base = so.base;
+    rng.cur = so.cur;
+    ng = (uint32_t)so.value;
+    S.status = so.status;
   }
 
   // add_error (error.rs:267-302): one Bernoulli(target / (L - pos)) per position.  32 positions are
@@ -318,7 +319,7 @@ __device__ void process_read(const ReadKernelParams& P, WarpSmem* ws, uint32_t g
       const bool inb = pi < nlim;
       const double rem = (double)(L - pi);
       const bool brk = target < 0.0 || target > rem;
-      const bool gl = (g < ng) && (pi == gbegin) && !(lane == 0 && glitch_checked);
+      const bool gl = (pi == gbegin) && !(lane == 0 && glitch_checked);
       const double p = target / rem;
       const bool one = (p == 1.0);
       const uint64_t v = rng.peek64(rng.cur + 2 * (uint64_t)lane);
@@ -339,29 +340,80 @@ __device__ void process_read(const ReadKernelParams& P, WarpSmem* ws, uint32_t g
         glitch_checked = false;
       }
       if (!(ff & 1u)) break;  // pos == L - k
-      if (ff & 2u) {          // glitch due at pos (error.rs:282-287)
-        GlitchRec gr = grec[g];
-        target -= (double)add_change(S, ws, P, gwarp, gr.begin, gr.end, gseq + gr.seq_off, gr.seq_len, lane);
+      uint64_t ob, oe, olen;
+      const uint8_t* oseq;
+      const bool is_glitch = (ff & 2u) != 0;
+      if (is_glitch) {  // glitch due at pos (error.rs:282-287)
+        const GlitchRec gr = grec[g];
+        ob = gr.begin;
+        oe = gr.end;
+        oseq = gseq + gr.seq_off;
+        olen = gr.seq_len;
         ++g;
         gbegin = (g < ng) ? grec[g].begin : ~0ULL;
-        glitch_checked = true;
-        if (S.status) break;
-        continue;  // same pos again, with the new target, glitch check done
+      } else {
+        if (ff & 4u) break;  // error.rs:289-291
+        if (!(ff & 8u)) rng.cur += 2;
+        // Error::add_errors_to_kmer (src/model/error.rs:93-107) -> ws->alt
+        const uint8_t* kmer = raw + pos;
+        int key = -1;
+        __syncwarp();
+        if (M.em_index) {  // 2-bit code of the k-mer; any byte outside ACGT misses the table
+          uint32_t part = 0, bad = 0;
+          if ((uint32_t)lane < k) {
+            uint8_t c = kmer[lane];
+            uint32_t s = c == 'A' ? 0u : c == 'C' ? 1u : c == 'G' ? 2u : c == 'T' ? 3u : 4u;
+            bad = s > 3u;
+            part = (s & 3u) << (2 * (k - 1 - lane));
+          }
+          uint32_t code = __reduce_or_sync(0xffffffffu, part);
+          if (!__any_sync(0xffffffffu, bad)) key = M.em_index[code];
+        }
+        if (key >= 0) {
+          so = stage_alt_from_table(rng, M, ws, key);
+          rng.base = so.base;
+          rng.cur = so.cur;
+          olen = so.value;
+        } else {  // random_error (src/model/error.rs:116-135)
+          const uint32_t ep = (uint32_t)rng.gen_range_u64(0, k - 1);
+          const uint32_t kind = rng.gen_range_u32(1, 3);  // 1 substitution, 2 insertion, 3 deletion
+          uint8_t nb = 0;
+          if (kind == 1) nb = rng.random_base_diff(kmer[ep]);
+          else if (kind == 2) nb = rng.random_base();
+          const uint32_t n = kind == 1 ? k : (kind == 2 ? k + 1 : k - 1);
+          if ((uint32_t)lane < n) {
+            const uint32_t i = lane;
+            uint8_t c;
+            if (kind == 1) c = (i == ep) ? nb : kmer[i];
+            else if (kind == 2) c = (i < ep) ? kmer[i] : (i == ep ? nb : kmer[i - 1]);
+            else c = (i < ep) ? kmer[i] : kmer[i + 1];
+            ws->alt[i] = c;
+          }
+          __syncwarp();
+          olen = n;
+        }
+        ob = pos;
+        oe = pos + k;
+        oseq = ws->alt;
       }
-      if (ff & 4u) break;  // error.rs:289-291
-      if (!(ff & 8u)) rng.cur += 2;
-      uint32_t alen = make_alt(rng, M, ws, raw + pos, lane);
-      target -= (double)add_change(S, ws, P, gwarp, pos, pos + k, ws->alt, alen, lane);
+      target -= (double)add_change(S, ws, P, gwarp, ob, oe, oseq, olen, lane);
       if (S.status) break;
-      if (target < 0.0 || target > (double)(L - pos)) break;  // error.rs:298-300
-      pos += 1;
-      glitch_checked = false;
+      if (is_glitch) {
+        glitch_checked = true;  // same pos again, with the new target, glitch check done
+      } else {
+        if (target < 0.0 || target > (double)(L - pos)) break;  // error.rs:298-300
+        pos += 1;
+        glitch_checked = false;
+      }
     }
   }
 
   // ---- K5: tail of the stitch (error.rs:241-246) ----
   if (S.status == ST_OK) {
-    st_finalize_last(S);
+    if (S.has_last && S.l_emit) {
+      S.real_edit += S.ledit;
+      S.pos_in_raw = S.le;
+    }
     if (S.pos_in_raw < L) st_emit_gap(S, L, lane);
   }
   __syncwarp();
@@ -371,7 +423,7 @@ __device__ void process_read(const ReadKernelParams& P, WarpSmem* ws, uint32_t g
     P.cig_len[ridx] = S.status ? 0 : S.cig_len;
     P.q_cursor[ridx] = rng.cur;
     P.real_id[ridx] = (1.0 - ((double)S.real_edit / (double)L)) * 100.0;  // error.rs:246, mod.rs:289
-    P.status[ridx] = (uint32_t)S.status;
+    P.status[ridx] = S.status;
   }
 }
 
