@@ -396,6 +396,7 @@ static int plan(rr_ctx* ctx) {
     if (d.has_chimera && (rc = frag_len(ctx, d.ctype, d.cref_idx, d.cstart, d.cend, f2))) return rc;
     if (!(d.identity <= 1.0 && d.identity >= -1.0)) return fail(ctx, RR_ERR_ARG, "rr_upload: identity outside [0,1]");
     uint64_t rcap = 2ULL * M.k + f1 + f2 + 2 * adapters;
+    if (rcap >= (1ULL << 30)) return fail(ctx, RR_ERR_UNSUPPORTED, "rr_upload: a single read of 2^30 bases or more");
     raw_cap[i] = rcap;
     ctx->max_raw_cap = std::max(ctx->max_raw_cap, rcap);
     double target = std::max(0.0, (1.0 - d.identity)) * (double)rcap;
@@ -667,7 +668,8 @@ __global__ void rr_debug_rng_kernel(uint64_t seed, uint64_t first, uint32_t n, u
   __shared__ uint32_t words[RNG_WORDS + 8];
   WarpRng rng;
   rng.seed(seed, words, threadIdx.x & 31);
-  rng.cur = first;
+  rng.set_cursor(rng.base, first);
+  rng.refill();
   for (uint32_t i = 0; i < n; ++i) {
     uint32_t v = rng.next_u32();
     if (threadIdx.x == 0) out[i] = v;

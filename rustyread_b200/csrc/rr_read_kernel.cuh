@@ -96,7 +96,7 @@ __device__ __noinline__ StageOut stage_assemble(WarpRng rng, const ReadKernelPar
   __syncwarp();
   StageOut o;
   o.base = rng.base;
-  o.cur = rng.cur;
+  o.cur = rng.cursor();
   o.value = L;
   o.status = ST_OK;
   return o;
@@ -134,7 +134,7 @@ __device__ __noinline__ StageOut stage_glitches(WarpRng rng, const ReadKernelPar
   __syncwarp();
   StageOut o;
   o.base = rng.base;
-  o.cur = rng.cur;
+  o.cur = rng.cursor();
   o.value = ng;
   o.status = status;
   return o;
@@ -160,7 +160,7 @@ __device__ __noinline__ StageOut stage_alt_from_table(WarpRng rng, const DeviceM
   __syncwarp();
   StageOut o;
   o.base = rng.base;
-  o.cur = rng.cur;
+  o.cur = rng.cursor();
   o.value = n;
   o.status = ST_OK;
   return o;
@@ -169,21 +169,22 @@ __device__ __noinline__ StageOut stage_alt_from_table(WarpRng rng, const DeviceM
 // State of `changes.last()` plus the streamed stitch of sequence() (src/simulate/error.rs:219-246).
 // A Change only ever grows by appending to seq / cigar (merge, error.rs:105-152), and only the last
 // one can change, so err / CIGAR are written once, in order, as the walk proceeds.
+// All positions are 32-bit: the host refuses reads whose raw capacity reaches 2^31 bases.
 struct Stitch {
   const uint8_t* raw;
-  uint64_t L;
   uint8_t* err;
   uint8_t* cig;
-  uint64_t cap;
-  uint64_t err_len, cig_len;
-  uint64_t pos_in_raw;   // sequence(): end of the last emitted change
-  uint64_t real_edit;
+  uint32_t L;
+  uint32_t cap;
+  uint32_t err_len, cig_len;
+  uint32_t pos_in_raw;   // sequence(): end of the last emitted change
+  uint32_t real_edit;
   bool has_last, l_emit;
-  uint64_t lb, le, lseq_len, ledit;
+  uint32_t lb, le, lseq_len, ledit;
   uint32_t status;
 };
 
-__device__ __forceinline__ bool st_reserve(Stitch& S, uint64_t n_err, uint64_t n_cig) {
+__device__ __forceinline__ bool st_reserve(Stitch& S, uint32_t n_err, uint32_t n_cig) {
   if (S.err_len + n_err > S.cap || S.cig_len + n_cig > S.cap) {
     S.status = ST_OUT_OVERFLOW;
     return false;
@@ -191,14 +192,14 @@ __device__ __forceinline__ bool st_reserve(Stitch& S, uint64_t n_err, uint64_t n
   return true;
 }
 
-__device__ __forceinline__ void st_emit_gap(Stitch& S, uint64_t upto, int lane) {  // raw[pos_in_raw..upto) copied, '=' in the CIGAR
+__device__ __forceinline__ void st_emit_gap(Stitch& S, uint32_t upto, int lane) {  // raw[pos_in_raw..upto) copied, '=' in the CIGAR
   if (upto <= S.pos_in_raw) return;
-  uint64_t n = upto - S.pos_in_raw;
+  uint32_t n = upto - S.pos_in_raw;
   if (!st_reserve(S, n, n)) return;
   const uint8_t* src = S.raw + S.pos_in_raw;
   uint8_t* de = S.err + S.err_len;
   uint8_t* dc = S.cig + S.cig_len;
-  for (uint64_t i = lane; i < n; i += 32) {
+  for (uint32_t i = lane; i < n; i += 32) {
     de[i] = src[i];
     dc[i] = '=';
   }
@@ -206,26 +207,26 @@ __device__ __forceinline__ void st_emit_gap(Stitch& S, uint64_t upto, int lane) 
   S.cig_len += n;
 }
 
-__device__ __forceinline__ void st_emit_seq(Stitch& S, const uint8_t* q, uint64_t n, int lane) {
+__device__ __forceinline__ void st_emit_seq(Stitch& S, const uint8_t* q, uint32_t n, int lane) {
   if (!st_reserve(S, n, 0)) return;
   uint8_t* de = S.err + S.err_len;
-  for (uint64_t i = lane; i < n; i += 32) de[i] = q[i];
+  for (uint32_t i = lane; i < n; i += 32) de[i] = q[i];
   S.err_len += n;
 }
 
 // AbsChanges::add_change (src/simulate/error.rs:173-193) with contain / overlap / merge /
 // update_align (error.rs:83-164).  Returns the edit count to subtract from the target.
 // One alignment call site: the merge and the push cases only differ in which slices are aligned.
-__device__ __forceinline__ uint64_t add_change(Stitch& S, WarpSmem* ws, const ReadKernelParams& P, uint32_t gwarp, uint64_t ob, uint64_t oe,
-                                               const uint8_t* oseq, uint64_t olen, int lane) {
+__device__ __forceinline__ uint32_t add_change(Stitch& S, WarpSmem* ws, const ReadKernelParams& P, uint32_t gwarp, uint32_t ob, uint32_t oe,
+                                               const uint8_t* oseq, uint32_t olen, int lane) {
   bool merge = false;
-  uint64_t es = 0, rs, re;
+  uint32_t es = 0, rs, re;
   if (S.has_last) {
-    const uint64_t l_end_err = S.lb + S.lseq_len;
+    const uint32_t l_end_err = S.lb + S.lseq_len;
     if (oe <= l_end_err || oe <= S.le || ob + olen <= l_end_err) return 0;  // contain (error.rs:83-88)
     if (ob < l_end_err || ob < S.le) {                                       // overlap -> merge (error.rs:105-152)
       merge = true;
-      const uint64_t old_end = S.le;
+      const uint32_t old_end = S.le;
       if (ob < l_end_err) {
         es = l_end_err - ob;  // olen > es holds because the change is not contained
         S.le = S.le + oe - ob - es;
@@ -255,10 +256,10 @@ __device__ __forceinline__ uint64_t add_change(Stitch& S, WarpSmem* ws, const Re
     S.ledit = 0;
     if (S.l_emit) st_emit_gap(S, ob, lane);
   }
-  const uint64_t add = olen - es;
+  const uint32_t add = olen - es;
   if (S.l_emit) st_emit_seq(S, oseq + es, add, lane);
   if (S.status) return 0;
-  const uint64_t a = warp_align(ws, P, gwarp, oseq + es, (uint32_t)add, S.raw + rs, (uint32_t)(re - rs),
+  const uint64_t a = warp_align(ws, P, gwarp, oseq + es, add, S.raw + rs, re - rs,
                                 S.l_emit ? S.cig + S.cig_len : nullptr, S.cap - S.cig_len, lane);
   if (align_status(a)) { S.status = align_status(a); return 0; }
   if (S.l_emit) S.cig_len += align_nops(a);
@@ -274,16 +275,15 @@ __device__ __forceinline__ void process_read(const ReadKernelParams& P, WarpSmem
 
   uint8_t* raw = P.raw + P.raw_off[ridx];
   StageOut so = stage_assemble(rng, P, ws, ridx, raw);
-  rng.base = so.base;
-  rng.cur = so.cur;
-  const uint64_t L = so.value;
+  rng.set_cursor(so.base, so.cur);
+  const uint32_t L = (uint32_t)so.value;
 
   Stitch S;
   S.raw = raw;
   S.L = L;
   S.err = P.err + P.out_off[ridx];
   S.cig = P.cig + P.out_off[ridx];
-  S.cap = P.out_off[ridx + 1] - P.out_off[ridx];
+  S.cap = (uint32_t)(P.out_off[ridx + 1] - P.out_off[ridx]);
   S.err_len = S.cig_len = 0;
   S.pos_in_raw = 0;
   S.real_edit = 0;
@@ -299,8 +299,7 @@ __device__ __forceinline__ void process_read(const ReadKernelParams& P, WarpSmem
   uint32_t ng = 0;
   if (M.has_distance) {
     so = stage_glitches(rng, P, gwarp, L);
-    rng.base = so.base;
-    rng.cur = so.cur;
+    rng.set_cursor(so.base, so.cur);
     ng = (uint32_t)so.value;
     S.status = so.status;
   }
@@ -308,26 +307,26 @@ __device__ __forceinline__ void process_read(const ReadKernelParams& P, WarpSmem
   // add_error (error.rs:267-302): one Bernoulli(target / (L - pos)) per position.  32 positions are
   // tried at once against the current target; the first lane with an event wins.
   if (S.status == ST_OK) {
-    const uint64_t nlim = L - k;
-    uint64_t pos = 0;
+    const uint32_t nlim = L - k;
+    uint32_t pos = 0;
     uint32_t g = 0;
-    uint64_t gbegin = ng ? grec[0].begin : ~0ULL;
+    uint32_t gbegin = ng ? (uint32_t)grec[0].begin : ~0u;
     bool glitch_checked = false;
     while (pos < nlim) {
       rng.need(64);
-      const uint64_t pi = pos + (uint64_t)lane;
+      const uint32_t pi = pos + (uint32_t)lane;
       const bool inb = pi < nlim;
       const double rem = (double)(L - pi);
       const bool brk = target < 0.0 || target > rem;
       const bool gl = (pi == gbegin) && !(lane == 0 && glitch_checked);
       const double p = target / rem;
       const bool one = (p == 1.0);
-      const uint64_t v = rng.peek64(rng.cur + 2 * (uint64_t)lane);
+      const uint64_t v = rng.peek64_at(rng.off + 2 * (uint32_t)lane);
       const bool hit = one || v < bernoulli_threshold(p);
       const uint32_t m_any = __ballot_sync(0xffffffffu, !inb || gl || brk || hit);
       if (m_any == 0) {
         pos += 32;
-        rng.cur += 64;
+        rng.off += 64;
         glitch_checked = false;
         continue;
       }
@@ -335,25 +334,25 @@ __device__ __forceinline__ void process_read(const ReadKernelParams& P, WarpSmem
       const uint32_t fl = (inb ? 1u : 0u) | (gl ? 2u : 0u) | (brk ? 4u : 0u) | (one ? 8u : 0u);
       const uint32_t ff = __shfl_sync(0xffffffffu, fl, f);
       if (f > 0) {
-        pos += (uint64_t)f;
-        rng.cur += 2 * (uint64_t)f;
+        pos += (uint32_t)f;
+        rng.off += 2 * (uint32_t)f;
         glitch_checked = false;
       }
       if (!(ff & 1u)) break;  // pos == L - k
-      uint64_t ob, oe, olen;
+      uint32_t ob, oe, olen;
       const uint8_t* oseq;
       const bool is_glitch = (ff & 2u) != 0;
       if (is_glitch) {  // glitch due at pos (error.rs:282-287)
         const GlitchRec gr = grec[g];
-        ob = gr.begin;
-        oe = gr.end;
+        ob = (uint32_t)gr.begin;
+        oe = (uint32_t)gr.end;
         oseq = gseq + gr.seq_off;
         olen = gr.seq_len;
         ++g;
-        gbegin = (g < ng) ? grec[g].begin : ~0ULL;
+        gbegin = (g < ng) ? (uint32_t)grec[g].begin : ~0u;
       } else {
         if (ff & 4u) break;  // error.rs:289-291
-        if (!(ff & 8u)) rng.cur += 2;
+        if (!(ff & 8u)) rng.off += 2;
         // Error::add_errors_to_kmer (src/model/error.rs:93-107) -> ws->alt
         const uint8_t* kmer = raw + pos;
         int key = -1;
@@ -371,9 +370,8 @@ __device__ __forceinline__ void process_read(const ReadKernelParams& P, WarpSmem
         }
         if (key >= 0) {
           so = stage_alt_from_table(rng, M, ws, key);
-          rng.base = so.base;
-          rng.cur = so.cur;
-          olen = so.value;
+          rng.set_cursor(so.base, so.cur);
+          olen = (uint32_t)so.value;
         } else {  // random_error (src/model/error.rs:116-135)
           const uint32_t ep = (uint32_t)rng.gen_range_u64(0, k - 1);
           const uint32_t kind = rng.gen_range_u32(1, 3);  // 1 substitution, 2 insertion, 3 deletion
@@ -421,7 +419,7 @@ __device__ __forceinline__ void process_read(const ReadKernelParams& P, WarpSmem
     P.raw_len[ridx] = L;
     P.err_len[ridx] = S.status ? 0 : S.err_len;
     P.cig_len[ridx] = S.status ? 0 : S.cig_len;
-    P.q_cursor[ridx] = rng.cur;
+    P.q_cursor[ridx] = rng.cursor();
     P.real_id[ridx] = (1.0 - ((double)S.real_edit / (double)L)) * 100.0;  // error.rs:246, mod.rs:289
     P.status[ridx] = S.status;
   }
