@@ -127,6 +127,14 @@ int rr_upload(rr_ctx* ctx, uint64_t n, const rr_desc* descs);
 int rr_run(rr_ctx* ctx);
 int rr_download(rr_ctx* ctx, rr_batch* out);
 
+/* Asynchronous, double-buffered form, so that the host can format and write batch i (mod.rs:191-212) while
+ * batch i+1 is generated: rr_submit queues H2D + kernels and returns at once (at most two batches in flight);
+ * rr_collect waits for the OLDEST submitted batch and drains it through pinned memory on a copy stream, which
+ * overlaps the kernels of the batch submitted after it.  The result stays valid until that slot is reused,
+ * i.e. until the second rr_submit after the one that produced it.  rr_generate == rr_submit + rr_collect. */
+int rr_submit(rr_ctx* ctx, uint64_t n, const rr_desc* descs);
+int rr_collect(rr_ctx* ctx, rr_batch* out);
+
 /* number of kernel launches issued by this context so far, and device milliseconds spent in the
  * last rr_run (CUDA events on the context's stream): [0] whole run, [1] read kernel (assemble +
  * glitches + error walk + alignment + stitch), [2] qscore kernel, [3] pack kernels */

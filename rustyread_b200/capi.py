@@ -48,6 +48,8 @@ EXPORTS = {
     "rr_upload": (C.c_int, [C.c_void_p, C.c_uint64, C.c_void_p]),
     "rr_run": (C.c_int, [C.c_void_p]),
     "rr_download": (C.c_int, [C.c_void_p, C.POINTER(rr_batch)]),
+    "rr_submit": (C.c_int, [C.c_void_p, C.c_uint64, C.c_void_p]),
+    "rr_collect": (C.c_int, [C.c_void_p, C.POINTER(rr_batch)]),
     "rr_kernel_launches": (C.c_uint64, [C.c_void_p]),
     "rr_last_run_ms": (C.c_int, [C.c_void_p, C.POINTER(C.c_float)]),
     "rr_last_run_bases": (C.c_uint64, [C.c_void_p]),
@@ -221,6 +223,17 @@ class Context:
     def download(self):
         b = rr_batch()
         self._ck(self.lib.dll.rr_download(self.h, C.byref(b)))
+        return Batch(b)
+
+    def submit(self, descs):
+        """Asynchronous rr_generate, first half: queues H2D + kernels (at most two batches in flight)."""
+        descs = np.ascontiguousarray(descs, dtype=DESC_DTYPE)
+        self._ck(self.lib.dll.rr_submit(self.h, len(descs), descs.ctypes.data))
+
+    def collect(self):
+        """Second half: waits for the oldest submitted batch and drains it to pinned host memory."""
+        b = rr_batch()
+        self._ck(self.lib.dll.rr_collect(self.h, C.byref(b)))
         return Batch(b)
 
     def kernel_launches(self):

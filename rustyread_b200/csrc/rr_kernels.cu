@@ -55,11 +55,8 @@ struct rr_ctx {
   int device = 0;
   int n_sm = 0;
   cudaStream_t stream = nullptr;
-  cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
   std::string err;
   uint64_t launches = 0;
-  float last_ms[4] = {0, 0, 0, 0};
-  uint64_t last_bases = 0, last_bytes = 0;
 
   // models
   DeviceModels M{};
@@ -73,22 +70,34 @@ struct rr_ctx {
   DevBuf d_adapter;
   DevBuf d_q_tab_off, d_q_tab, d_q_dist_off, d_q_scores, d_q_cum, d_q_scale;
 
-  // batch
-  uint64_t n = 0;
-  std::vector<rr_desc> descs;
-  std::vector<uint64_t> h_raw_off, h_out_off;
-  std::vector<uint32_t> h_order;
-  double slack = 1.5;
-  uint64_t max_raw_cap = 0;
-  DevBuf d_descs, d_order, d_queue, d_raw_off, d_out_off, d_raw, d_err, d_cig;
-  DevBuf d_raw_len, d_err_len, d_cig_len, d_q_cursor, d_real_id, d_status, d_packed_off, d_totals;
-  DevBuf d_seq, d_qual;
+  // Up to two batches in flight (rr_submit / rr_collect): per-batch state lives in a slot; the big working
+  // arenas (raw / err / cigar) and the per-warp scratch are shared because kernels of consecutive batches are
+  // serialised on the compute stream, while the D2H of batch i (copy stream) overlaps the kernels of batch i+1.
+  struct Slot {
+    uint64_t n = 0;
+    std::vector<rr_desc> descs;
+    std::vector<uint64_t> h_raw_off, h_out_off;
+    std::vector<uint32_t> h_order;
+    double slack = 1.5;
+    uint64_t sc_grec_cap = 0, sc_gseq_cap = 0;
+    uint32_t read_grid = 0;
+    DevBuf d_descs, d_order, d_queue, d_raw_off, d_out_off;
+    DevBuf d_raw_len, d_err_len, d_cig_len, d_q_cursor, d_real_id, d_status, d_packed_off, d_totals;
+    DevBuf d_seq, d_qual;
+    PinBuf h_seq, h_qual, h_off, h_len, h_id, h_totals, h_status;
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t done = nullptr;
+    bool prepared = false, enqueued = false, ran = false;
+    float ms[4] = {0, 0, 0, 0};
+    uint64_t bases = 0, bytes = 0;
+  };
+  Slot slot[2];
+  uint64_t n_submitted = 0, n_collected = 0;
+  int last_slot = 0;  // slot of the most recently completed run (debug fetch, timings)
+  cudaStream_t copy_stream = nullptr;
+  DevBuf d_raw, d_err, d_cig;
   DevBuf d_sc_rows, d_sc_ops, d_sc_grec, d_sc_gseq;
   uint64_t sc_rows_cap = 32768, sc_ops_cap = 8192, sc_grec_cap = 0, sc_gseq_cap = 0;
-  uint32_t n_warps = 0, read_grid = 0;
-  bool ran = false;
-
-  PinBuf h_seq, h_qual, h_off, h_len, h_id, h_totals, h_status;
 };
 
 static int fail(rr_ctx* c, int code, const std::string& msg) {
@@ -138,8 +147,12 @@ RR_API int rr_create(int device, rr_ctx** out) {
   ctx = new rr_ctx();
   ctx->device = device;
   ctx->n_sm = prop.multiProcessorCount;
-  if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return fail(nullptr, RR_ERR_CUDA, "cudaStreamCreate failed"); }
-  for (auto& ev : ctx->ev) cudaEventCreate(&ev);
+  if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return fail(nullptr, RR_ERR_CUDA, "cudaStreamCreate failed"); }
+  for (auto& sl : ctx->slot) {
+    for (auto& ev : sl.ev) cudaEventCreate(&ev);
+    cudaEventCreateWithFlags(&sl.done, cudaEventDisableTiming);
+  }
   *out = ctx;
   return RR_OK;
 }
@@ -148,27 +161,33 @@ RR_API void rr_destroy(rr_ctx* ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
+  cudaStreamSynchronize(ctx->copy_stream);
   DevBuf* bufs[] = {&ctx->d_ref, &ctx->d_ref_off, &ctx->d_ref_circ, &ctx->d_em_index, &ctx->d_em_alt_begin, &ctx->d_em_alt_off,
                     &ctx->d_em_alt_bytes, &ctx->d_em_cum, &ctx->d_em_scale, &ctx->d_adapter, &ctx->d_q_tab_off, &ctx->d_q_tab,
-                    &ctx->d_q_dist_off, &ctx->d_q_scores, &ctx->d_q_cum, &ctx->d_q_scale, &ctx->d_descs, &ctx->d_order, &ctx->d_queue,
-                    &ctx->d_raw_off, &ctx->d_out_off, &ctx->d_raw, &ctx->d_err, &ctx->d_cig, &ctx->d_raw_len, &ctx->d_err_len,
-                    &ctx->d_cig_len, &ctx->d_q_cursor, &ctx->d_real_id, &ctx->d_status, &ctx->d_packed_off, &ctx->d_totals,
-                    &ctx->d_seq, &ctx->d_qual, &ctx->d_sc_rows, &ctx->d_sc_ops, &ctx->d_sc_grec, &ctx->d_sc_gseq};
+                    &ctx->d_q_dist_off, &ctx->d_q_scores, &ctx->d_q_cum, &ctx->d_q_scale, &ctx->d_raw, &ctx->d_err, &ctx->d_cig,
+                    &ctx->d_sc_rows, &ctx->d_sc_ops, &ctx->d_sc_grec, &ctx->d_sc_gseq};
   for (auto* b : bufs) b->release();
-  PinBuf* pins[] = {&ctx->h_seq, &ctx->h_qual, &ctx->h_off, &ctx->h_len, &ctx->h_id, &ctx->h_totals, &ctx->h_status};
-  for (auto* b : pins) b->release();
-  for (auto& ev : ctx->ev) if (ev) cudaEventDestroy(ev);
+  for (auto& sl : ctx->slot) {
+    DevBuf* sb[] = {&sl.d_descs, &sl.d_order, &sl.d_queue, &sl.d_raw_off, &sl.d_out_off, &sl.d_raw_len, &sl.d_err_len, &sl.d_cig_len,
+                    &sl.d_q_cursor, &sl.d_real_id, &sl.d_status, &sl.d_packed_off, &sl.d_totals, &sl.d_seq, &sl.d_qual};
+    for (auto* b : sb) b->release();
+    PinBuf* pins[] = {&sl.h_seq, &sl.h_qual, &sl.h_off, &sl.h_len, &sl.h_id, &sl.h_totals, &sl.h_status};
+    for (auto* b : pins) b->release();
+    for (auto& ev : sl.ev) if (ev) cudaEventDestroy(ev);
+    if (sl.done) cudaEventDestroy(sl.done);
+  }
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
+  if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
   delete ctx;
 }
 
 RR_API const char* rr_last_error(const rr_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
 RR_API uint64_t rr_kernel_launches(const rr_ctx* ctx) { return ctx ? ctx->launches : 0; }
-RR_API uint64_t rr_last_run_bases(const rr_ctx* ctx) { return ctx ? ctx->last_bases : 0; }
+RR_API uint64_t rr_last_run_bases(const rr_ctx* ctx) { return ctx ? ctx->slot[ctx->last_slot].bases : 0; }
 RR_API void* rr_stream(const rr_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
 RR_API int rr_last_run_ms(const rr_ctx* ctx, float* ms4) {
   if (!ctx || !ms4) return RR_ERR_ARG;
-  for (int i = 0; i < 4; ++i) ms4[i] = ctx->last_ms[i];
+  for (int i = 0; i < 4; ++i) ms4[i] = ctx->slot[ctx->last_slot].ms[i];
   return RR_OK;
 }
 
@@ -362,6 +381,7 @@ RR_API int rr_set_glitch(rr_ctx* ctx, double rate, double size, double skip) {
 
 // ---- batch planning ------------------------------------------------------------------------------------------
 static inline uint64_t align16(uint64_t x) { return (x + 15) & ~15ULL; }
+typedef rr_ctx::Slot Slot;
 
 static int frag_len(rr_ctx* ctx, uint32_t type, uint32_t ref_idx, uint64_t start, uint64_t end, uint64_t& out) {
   if (type == RR_JUNK || type == RR_RANDOM) { out = end; return RR_OK; }
@@ -378,18 +398,17 @@ static int frag_len(rr_ctx* ctx, uint32_t type, uint32_t ref_idx, uint64_t start
   return RR_OK;
 }
 
-static int plan(rr_ctx* ctx) {
-  const uint64_t n = ctx->n;
+static int plan(rr_ctx* ctx, Slot& sl) {
+  const uint64_t n = sl.n;
   const DeviceModels& M = ctx->M;
   const uint64_t adapters = (uint64_t)M.start_len + M.end_len;
-  ctx->h_raw_off.assign(n + 1, 0);
-  ctx->h_out_off.assign(n + 1, 0);
-  ctx->h_order.resize(n);
-  ctx->max_raw_cap = 0;
+  sl.h_raw_off.assign(n + 1, 0);
+  sl.h_out_off.assign(n + 1, 0);
+  sl.h_order.resize(n);
   std::vector<uint64_t> raw_cap(n);
   double max_ng = 0;
   for (uint64_t i = 0; i < n; ++i) {
-    const rr_desc& d = ctx->descs[i];
+    const rr_desc& d = sl.descs[i];
     uint64_t f1 = 0, f2 = 0;
     int rc = frag_len(ctx, d.type, d.ref_idx, d.start, d.end, f1);
     if (rc) return rc;
@@ -398,232 +417,297 @@ static int plan(rr_ctx* ctx) {
     uint64_t rcap = 2ULL * M.k + f1 + f2 + 2 * adapters;
     if (rcap >= (1ULL << 30)) return fail(ctx, RR_ERR_UNSUPPORTED, "rr_upload: a single read of 2^30 bases or more");
     raw_cap[i] = rcap;
-    ctx->max_raw_cap = std::max(ctx->max_raw_cap, rcap);
     double target = std::max(0.0, (1.0 - d.identity)) * (double)rcap;
     double ng = 0, gl = 0;
     if (M.has_distance) {
       ng = (double)rcap / (ctx->glitch_mean_dist + 1.0);
-      ng = (ng + 6.0 * std::sqrt(ng) + 30.0) * ctx->slack;
+      ng = (ng + 6.0 * std::sqrt(ng) + 30.0) * sl.slack;
       gl = ng * (ctx->glitch_mean_size + 1.0);
       max_ng = std::max(max_ng, ng);
     }
-    uint64_t ocap = align16(rcap + (uint64_t)std::ceil(target) + (uint64_t)gl + (uint64_t)(64 * ctx->slack) + ALT_MAX + 16);
-    ctx->h_raw_off[i + 1] = ctx->h_raw_off[i] + align16(rcap + 16);
-    ctx->h_out_off[i + 1] = ctx->h_out_off[i] + ocap;
+    uint64_t ocap = align16(rcap + (uint64_t)std::ceil(target) + (uint64_t)gl + (uint64_t)(64 * sl.slack) + ALT_MAX + 16);
+    sl.h_raw_off[i + 1] = sl.h_raw_off[i] + align16(rcap + 16);
+    sl.h_out_off[i + 1] = sl.h_out_off[i] + ocap;
   }
-  std::iota(ctx->h_order.begin(), ctx->h_order.end(), 0u);
-  std::stable_sort(ctx->h_order.begin(), ctx->h_order.end(), [&](uint32_t a, uint32_t b) { return raw_cap[a] > raw_cap[b]; });
-  ctx->sc_grec_cap = (uint64_t)max_ng + 8;
-  ctx->sc_gseq_cap = align16((uint64_t)(max_ng * (ctx->glitch_mean_size + 1.0)) + 64);
+  std::iota(sl.h_order.begin(), sl.h_order.end(), 0u);
+  std::stable_sort(sl.h_order.begin(), sl.h_order.end(), [&](uint32_t a, uint32_t b) { return raw_cap[a] > raw_cap[b]; });
+  sl.sc_grec_cap = (uint64_t)max_ng + 8;
+  sl.sc_gseq_cap = align16((uint64_t)(max_ng * (ctx->glitch_mean_size + 1.0)) + 64);
   return RR_OK;
 }
 
-static int upload_plan(rr_ctx* ctx) {
-  const uint64_t n = ctx->n;
-  if (!upload(ctx, ctx->d_raw_off, ctx->h_raw_off) || !upload(ctx, ctx->d_out_off, ctx->h_out_off) || !upload(ctx, ctx->d_order, ctx->h_order))
-    return fail(ctx, RR_ERR_CUDA, "rr_upload: H2D of the plan failed");
-  ENSURE(ctx->d_raw, ctx->h_raw_off[n] + 16);
-  ENSURE(ctx->d_err, ctx->h_out_off[n] + 16);
-  ENSURE(ctx->d_cig, ctx->h_out_off[n] + 16);
-  // persistent grid: 4 blocks of 8 warps per SM, fewer if the batch is small
+// H2D of the plan + (re)allocation of everything the kernels of this batch touch.  Reallocation of a SHARED buffer
+// must not race with kernels of the other slot still in flight: the caller drains the compute stream first when needed.
+static int upload_plan(rr_ctx* ctx, Slot& sl) {
+  const uint64_t n = sl.n;
   uint32_t want_blocks = (uint32_t)std::min<uint64_t>((uint64_t)ctx->n_sm * 4, (n + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK);
-  ctx->read_grid = std::max<uint32_t>(1, want_blocks);
-  ctx->n_warps = ctx->read_grid * WARPS_PER_BLOCK;
-  ENSURE(ctx->d_sc_rows, (uint64_t)ctx->n_warps * ctx->sc_rows_cap * 8);
-  ENSURE(ctx->d_sc_ops, (uint64_t)ctx->n_warps * ctx->sc_ops_cap);
-  ENSURE(ctx->d_sc_grec, (uint64_t)ctx->n_warps * ctx->sc_grec_cap * sizeof(GlitchRec));
-  ENSURE(ctx->d_sc_gseq, (uint64_t)ctx->n_warps * ctx->sc_gseq_cap);
+  sl.read_grid = std::max<uint32_t>(1, want_blocks);  // persistent grid: 4 blocks of 8 warps per SM, fewer if the batch is small
+  const uint64_t n_warps = (uint64_t)ctx->n_sm * 4 * WARPS_PER_BLOCK;
+  const uint64_t grec = std::max(ctx->sc_grec_cap, sl.sc_grec_cap), gseq = std::max(ctx->sc_gseq_cap, sl.sc_gseq_cap);
+  const bool grow = sl.h_raw_off[n] + 16 > ctx->d_raw.cap || sl.h_out_off[n] + 16 > ctx->d_err.cap || sl.h_out_off[n] + 16 > ctx->d_cig.cap ||
+                    n_warps * ctx->sc_rows_cap * 8 > ctx->d_sc_rows.cap || n_warps * ctx->sc_ops_cap > ctx->d_sc_ops.cap ||
+                    n_warps * grec * sizeof(GlitchRec) > ctx->d_sc_grec.cap || n_warps * gseq > ctx->d_sc_gseq.cap;
+  if (grow) CK(cudaStreamSynchronize(ctx->stream));  // another batch may still be using the shared arenas
+  ctx->sc_grec_cap = grec;
+  ctx->sc_gseq_cap = gseq;
+  ENSURE(ctx->d_raw, sl.h_raw_off[n] + 16);
+  ENSURE(ctx->d_err, sl.h_out_off[n] + 16);
+  ENSURE(ctx->d_cig, sl.h_out_off[n] + 16);
+  ENSURE(ctx->d_sc_rows, n_warps * ctx->sc_rows_cap * 8);
+  ENSURE(ctx->d_sc_ops, n_warps * ctx->sc_ops_cap);
+  ENSURE(ctx->d_sc_grec, n_warps * ctx->sc_grec_cap * sizeof(GlitchRec));
+  ENSURE(ctx->d_sc_gseq, n_warps * ctx->sc_gseq_cap);
+  ENSURE(sl.d_raw_off, (n + 1) * 8);
+  ENSURE(sl.d_out_off, (n + 1) * 8);
+  ENSURE(sl.d_order, n * 4);
+  // worst-case packed size (capacities), so that no host round trip is needed between the kernels of a batch
+  ENSURE(sl.d_seq, sl.h_out_off[n] + 16);
+  ENSURE(sl.d_qual, sl.h_out_off[n] + 16);
+  CK(cudaMemcpyAsync(sl.d_raw_off.p, sl.h_raw_off.data(), (n + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemcpyAsync(sl.d_out_off.p, sl.h_out_off.data(), (n + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemcpyAsync(sl.d_order.p, sl.h_order.data(), n * 4, cudaMemcpyHostToDevice, ctx->stream));
   return RR_OK;
 }
 
-RR_API int rr_upload(rr_ctx* ctx, uint64_t n, const rr_desc* descs) {
-  if (!ctx) return RR_ERR_ARG;
+// plan + H2D of one batch into a slot (no kernels yet)
+static int prepare(rr_ctx* ctx, Slot& sl, uint64_t n, const rr_desc* descs) {
   if (!(ctx->have_refs && ctx->have_error && ctx->have_qscore && ctx->have_adapter && ctx->have_glitch))
     return fail(ctx, RR_ERR_ARG, "rr_upload: references and all four models must be set first");
   if (n == 0 || !descs) return fail(ctx, RR_ERR_ARG, "rr_upload: empty batch");
   if (n > 0x7fffffffULL) return fail(ctx, RR_ERR_UNSUPPORTED, "rr_upload: more than 2^31 reads in one batch");
   CK(cudaSetDevice(ctx->device));
-  ctx->ran = false;
-  ctx->n = n;
-  ctx->descs.assign(descs, descs + n);
-  ctx->slack = 1.5;
-  int rc = plan(ctx);
+  sl.prepared = sl.enqueued = sl.ran = false;
+  sl.n = n;
+  sl.descs.assign(descs, descs + n);
+  sl.slack = 1.5;
+  int rc = plan(ctx, sl);
   if (rc) return rc;
-  ENSURE(ctx->d_descs, n * sizeof(rr_desc));
-  CK(cudaMemcpyAsync(ctx->d_descs.p, descs, n * sizeof(rr_desc), cudaMemcpyHostToDevice, ctx->stream));
-  rc = upload_plan(ctx);
+  ENSURE(sl.d_descs, n * sizeof(rr_desc));
+  ENSURE(sl.d_queue, 16);
+  ENSURE(sl.d_raw_len, n * 8);
+  ENSURE(sl.d_err_len, n * 8);
+  ENSURE(sl.d_cig_len, n * 8);
+  ENSURE(sl.d_q_cursor, n * 8);
+  ENSURE(sl.d_real_id, n * 8);
+  ENSURE(sl.d_status, n * 4);
+  ENSURE(sl.d_packed_off, (n + 1) * 8);
+  ENSURE(sl.d_totals, 32);
+  ENSURE(sl.h_totals, 32);
+  ENSURE(sl.h_status, n * 4);
+  CK(cudaMemcpyAsync(sl.d_descs.p, sl.descs.data(), n * sizeof(rr_desc), cudaMemcpyHostToDevice, ctx->stream));
+  rc = upload_plan(ctx, sl);
   if (rc) return rc;
-  ENSURE(ctx->d_queue, 16);
-  ENSURE(ctx->d_raw_len, n * 8);
-  ENSURE(ctx->d_err_len, n * 8);
-  ENSURE(ctx->d_cig_len, n * 8);
-  ENSURE(ctx->d_q_cursor, n * 8);
-  ENSURE(ctx->d_real_id, n * 8);
-  ENSURE(ctx->d_status, n * 4);
-  ENSURE(ctx->d_packed_off, (n + 1) * 8);
-  ENSURE(ctx->d_totals, 32);
-  ENSURE(ctx->h_totals, 32);
-  CK(cudaStreamSynchronize(ctx->stream));
+  sl.prepared = true;
   return RR_OK;
 }
 
-static int launch_all(rr_ctx* ctx) {
-  const uint32_t n = (uint32_t)ctx->n;
+// queue the four kernels of a batch on the compute stream; returns without waiting
+static int enqueue(rr_ctx* ctx, Slot& sl) {
+  const uint32_t n = (uint32_t)sl.n;
   ReadKernelParams P{};
   P.M = ctx->M;
-  P.descs = ctx->d_descs.as<rr_desc>();
-  P.order = ctx->d_order.as<uint32_t>();
+  P.descs = sl.d_descs.as<rr_desc>();
+  P.order = sl.d_order.as<uint32_t>();
   P.n_reads = n;
-  P.queue = ctx->d_queue.as<uint32_t>();
-  P.raw_off = ctx->d_raw_off.as<uint64_t>();
-  P.out_off = ctx->d_out_off.as<uint64_t>();
+  P.queue = sl.d_queue.as<uint32_t>();
+  P.raw_off = sl.d_raw_off.as<uint64_t>();
+  P.out_off = sl.d_out_off.as<uint64_t>();
   P.raw = ctx->d_raw.as<uint8_t>();
   P.err = ctx->d_err.as<uint8_t>();
   P.cig = ctx->d_cig.as<uint8_t>();
-  P.raw_len = ctx->d_raw_len.as<uint64_t>();
-  P.err_len = ctx->d_err_len.as<uint64_t>();
-  P.cig_len = ctx->d_cig_len.as<uint64_t>();
-  P.q_cursor = ctx->d_q_cursor.as<uint64_t>();
-  P.real_id = ctx->d_real_id.as<double>();
-  P.status = ctx->d_status.as<uint32_t>();
+  P.raw_len = sl.d_raw_len.as<uint64_t>();
+  P.err_len = sl.d_err_len.as<uint64_t>();
+  P.cig_len = sl.d_cig_len.as<uint64_t>();
+  P.q_cursor = sl.d_q_cursor.as<uint64_t>();
+  P.real_id = sl.d_real_id.as<double>();
+  P.status = sl.d_status.as<uint32_t>();
   P.sc_rows = ctx->d_sc_rows.as<uint64_t>();  P.sc_rows_cap = ctx->sc_rows_cap;
   P.sc_ops = ctx->d_sc_ops.as<uint8_t>();     P.sc_ops_cap = ctx->sc_ops_cap;
   P.sc_grec = ctx->d_sc_grec.as<GlitchRec>(); P.sc_grec_cap = ctx->sc_grec_cap;
   P.sc_gseq = ctx->d_sc_gseq.as<uint8_t>();   P.sc_gseq_cap = ctx->sc_gseq_cap;
 
-  CK(cudaMemsetAsync(ctx->d_queue.p, 0, 16, ctx->stream));
-  CK(cudaEventRecord(ctx->ev[0], ctx->stream));
-  rr_read_kernel<<<ctx->read_grid, WARPS_PER_BLOCK * 32, 0, ctx->stream>>>(P);
+  CK(cudaMemsetAsync(sl.d_queue.p, 0, 16, ctx->stream));
+  CK(cudaEventRecord(sl.ev[0], ctx->stream));
+  rr_read_kernel<<<sl.read_grid, WARPS_PER_BLOCK * 32, 0, ctx->stream>>>(P);
   CK(cudaGetLastError());
-  CK(cudaEventRecord(ctx->ev[1], ctx->stream));
-  rr_scan_kernel<<<1, 1024, 0, ctx->stream>>>(ctx->d_err_len.as<uint64_t>(), ctx->d_status.as<uint32_t>(), n, ctx->M.k,
-                                              ctx->d_packed_off.as<uint64_t>(), ctx->d_totals.as<uint64_t>());
+  CK(cudaEventRecord(sl.ev[1], ctx->stream));
+  rr_scan_kernel<<<1, 1024, 0, ctx->stream>>>(sl.d_err_len.as<uint64_t>(), sl.d_status.as<uint32_t>(), n, ctx->M.k,
+                                              sl.d_packed_off.as<uint64_t>(), sl.d_totals.as<uint64_t>());
   CK(cudaGetLastError());
-  CK(cudaMemcpyAsync(ctx->h_totals.p, ctx->d_totals.p, 24, cudaMemcpyDeviceToHost, ctx->stream));
-  CK(cudaStreamSynchronize(ctx->stream));  // the packed size decides the output allocation
-  const uint64_t total = ctx->h_totals.as<uint64_t>()[0];
-  ENSURE(ctx->d_seq, total + 16);
-  ENSURE(ctx->d_qual, total + 16);
-
   QscoreKernelParams QP{};
   QP.Q = ctx->Q;
   QP.descs = P.descs;
   QP.order = P.order;
   QP.n_reads = n;
-  QP.queue = ctx->d_queue.as<uint32_t>() + 1;
+  QP.queue = sl.d_queue.as<uint32_t>() + 1;
   QP.out_off = P.out_off;
   QP.cig = P.cig;
   QP.cig_len = P.cig_len;
   QP.err_len = P.err_len;
   QP.q_cursor = P.q_cursor;
-  QP.packed_off = ctx->d_packed_off.as<uint64_t>();
-  QP.qual = ctx->d_qual.as<uint8_t>();
+  QP.packed_off = sl.d_packed_off.as<uint64_t>();
+  QP.qual = sl.d_qual.as<uint8_t>();
   QP.status = P.status;
   uint32_t qgrid = (uint32_t)std::min<uint64_t>((uint64_t)ctx->n_sm * 8, n);
   rr_qscore_kernel<<<qgrid, Q_THREADS, 0, ctx->stream>>>(QP);
   CK(cudaGetLastError());
-  CK(cudaEventRecord(ctx->ev[2], ctx->stream));
+  CK(cudaEventRecord(sl.ev[2], ctx->stream));
   PackKernelParams K{};
   K.n_reads = n;
   K.out_off = P.out_off;
   K.packed_off = QP.packed_off;
   K.err_len = P.err_len;
   K.err = P.err;
-  K.seq = ctx->d_seq.as<uint8_t>();
+  K.seq = sl.d_seq.as<uint8_t>();
   uint32_t pgrid = (uint32_t)std::min<uint64_t>((uint64_t)ctx->n_sm * 8, n);
   rr_pack_kernel<<<pgrid, 256, 0, ctx->stream>>>(K);
   CK(cudaGetLastError());
-  CK(cudaEventRecord(ctx->ev[3], ctx->stream));
-  CK(cudaStreamSynchronize(ctx->stream));
+  CK(cudaEventRecord(sl.ev[3], ctx->stream));
+  CK(cudaMemcpyAsync(sl.h_totals.p, sl.d_totals.p, 24, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaMemcpyAsync(sl.h_status.p, sl.d_status.p, (size_t)n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaEventRecord(sl.done, ctx->stream));
   ctx->launches += 4;
-  float a = 0, b = 0, c = 0, w = 0;
-  cudaEventElapsedTime(&w, ctx->ev[0], ctx->ev[3]);
-  cudaEventElapsedTime(&a, ctx->ev[0], ctx->ev[1]);
-  cudaEventElapsedTime(&b, ctx->ev[1], ctx->ev[2]);
-  cudaEventElapsedTime(&c, ctx->ev[2], ctx->ev[3]);
-  ctx->last_ms[0] = w; ctx->last_ms[1] = a; ctx->last_ms[2] = b; ctx->last_ms[3] = c;
-  ctx->last_bytes = total;
-  ctx->last_bases = ctx->h_totals.as<uint64_t>()[1];
+  sl.enqueued = true;
   return RR_OK;
 }
 
-RR_API int rr_run(rr_ctx* ctx) {
-  if (!ctx) return RR_ERR_ARG;
-  if (ctx->n == 0) return fail(ctx, RR_ERR_ARG, "rr_run: nothing uploaded");
-  CK(cudaSetDevice(ctx->device));
+// wait for the batch; on a capacity overflow re-plan with more slack and run again (synchronously)
+static int finish(rr_ctx* ctx, Slot& sl) {
   for (int attempt = 0; attempt < 6; ++attempt) {
-    int rc = launch_all(ctx);
-    if (rc) return rc;
-    // status of the qscore kernel may have changed after the scan: re-read the failure count cheaply
-    const uint64_t failed_scan = ctx->h_totals.as<uint64_t>()[2];
-    ENSURE(ctx->h_status, ctx->n * 4);
-    bool need_status = failed_scan != 0;
-    if (!need_status) {
-      // qscore failures are rare and fatal; detect them with one reduction-free pass over the status words
-      CK(cudaMemcpyAsync(ctx->h_status.p, ctx->d_status.p, ctx->n * 4, cudaMemcpyDeviceToHost, ctx->stream));
-      CK(cudaStreamSynchronize(ctx->stream));
-    } else {
-      CK(cudaMemcpyAsync(ctx->h_status.p, ctx->d_status.p, ctx->n * 4, cudaMemcpyDeviceToHost, ctx->stream));
-      CK(cudaStreamSynchronize(ctx->stream));
-    }
-    const uint32_t* st = ctx->h_status.as<uint32_t>();
+    CK(cudaEventSynchronize(sl.done));
+    float a = 0, b = 0, c = 0, w = 0;
+    cudaEventElapsedTime(&w, sl.ev[0], sl.ev[3]);
+    cudaEventElapsedTime(&a, sl.ev[0], sl.ev[1]);
+    cudaEventElapsedTime(&b, sl.ev[1], sl.ev[2]);
+    cudaEventElapsedTime(&c, sl.ev[2], sl.ev[3]);
+    sl.ms[0] = w; sl.ms[1] = a; sl.ms[2] = b; sl.ms[3] = c;
+    sl.bytes = sl.h_totals.as<uint64_t>()[0];
+    sl.bases = sl.h_totals.as<uint64_t>()[1];
+    const uint32_t* st = sl.h_status.as<uint32_t>();
     uint64_t grow = 0;
-    for (uint64_t i = 0; i < ctx->n; ++i) {
+    for (uint64_t i = 0; i < sl.n; ++i) {
       if (st[i] == ST_OK) continue;
       if (st[i] == ST_OUT_OVERFLOW || st[i] == ST_GLITCH_OVERFLOW) { ++grow; continue; }
       char buf[256];
       const char* what = st[i] == ST_ALIGN_TOO_LARGE ? "alignment window beyond the bit-vector scratch (2048 columns)"
                          : st[i] == ST_REF_PANIC     ? "slice out of range in Change::merge/update_align (the reference panics here)"
                                                      : "qscore window not in the model (reference: QualityNotMinimalCigarString)";
-      std::snprintf(buf, sizeof buf, "read %llu (seed %llu): %s", (unsigned long long)i, (unsigned long long)ctx->descs[i].seed, what);
+      std::snprintf(buf, sizeof buf, "read %llu (seed %llu): %s", (unsigned long long)i, (unsigned long long)sl.descs[i].seed, what);
+      sl.enqueued = false;
       return fail(ctx, RR_ERR_READ, buf);
     }
-    if (grow == 0) { ctx->ran = true; return RR_OK; }
-    ctx->slack *= 2.0;  // capacity estimate too small for `grow` reads: re-plan with more slack
-    rc = plan(ctx);
+    if (grow == 0) {
+      sl.ran = true;
+      sl.enqueued = false;
+      ctx->last_slot = (int)(&sl - ctx->slot);
+      return RR_OK;
+    }
+    sl.slack *= 2.0;  // capacity estimate too small for `grow` reads
+    int rc = plan(ctx, sl);
     if (rc) return rc;
-    rc = upload_plan(ctx);
+    rc = upload_plan(ctx, sl);
+    if (rc) return rc;
+    rc = enqueue(ctx, sl);
     if (rc) return rc;
   }
+  sl.enqueued = false;
   return fail(ctx, RR_ERR_READ, "rr_run: output capacity still too small after 6 attempts");
 }
 
-RR_API int rr_download(rr_ctx* ctx, rr_batch* out) {
-  if (!ctx || !out) return RR_ERR_ARG;
-  if (!ctx->ran) return fail(ctx, RR_ERR_ARG, "rr_download: no completed rr_run");
-  CK(cudaSetDevice(ctx->device));
-  const uint64_t n = ctx->n, total = ctx->last_bytes;
-  ENSURE(ctx->h_off, (n + 1) * 8);
-  ENSURE(ctx->h_len, n * 8);
-  ENSURE(ctx->h_id, n * 8);
-  ENSURE(ctx->h_seq, total + 16);
-  ENSURE(ctx->h_qual, total + 16);
-  CK(cudaMemcpyAsync(ctx->h_off.p, ctx->d_packed_off.p, (n + 1) * 8, cudaMemcpyDeviceToHost, ctx->stream));
-  CK(cudaMemcpyAsync(ctx->h_len.p, ctx->d_err_len.p, n * 8, cudaMemcpyDeviceToHost, ctx->stream));
-  CK(cudaMemcpyAsync(ctx->h_id.p, ctx->d_real_id.p, n * 8, cudaMemcpyDeviceToHost, ctx->stream));
+// D2H of the packed result on the copy stream (the batch's kernels are known to be complete)
+static int fetch(rr_ctx* ctx, Slot& sl, rr_batch* out) {
+  const uint64_t n = sl.n, total = sl.bytes;
+  ENSURE(sl.h_off, (n + 1) * 8);
+  ENSURE(sl.h_len, n * 8);
+  ENSURE(sl.h_id, n * 8);
+  ENSURE(sl.h_seq, total + 16);
+  ENSURE(sl.h_qual, total + 16);
+  cudaStream_t cs = ctx->copy_stream;
+  CK(cudaMemcpyAsync(sl.h_off.p, sl.d_packed_off.p, (n + 1) * 8, cudaMemcpyDeviceToHost, cs));
+  CK(cudaMemcpyAsync(sl.h_len.p, sl.d_err_len.p, n * 8, cudaMemcpyDeviceToHost, cs));
+  CK(cudaMemcpyAsync(sl.h_id.p, sl.d_real_id.p, n * 8, cudaMemcpyDeviceToHost, cs));
   if (total) {
-    CK(cudaMemcpyAsync(ctx->h_seq.p, ctx->d_seq.p, total, cudaMemcpyDeviceToHost, ctx->stream));
-    CK(cudaMemcpyAsync(ctx->h_qual.p, ctx->d_qual.p, total, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(sl.h_seq.p, sl.d_seq.p, total, cudaMemcpyDeviceToHost, cs));
+    CK(cudaMemcpyAsync(sl.h_qual.p, sl.d_qual.p, total, cudaMemcpyDeviceToHost, cs));
   }
-  CK(cudaStreamSynchronize(ctx->stream));
+  CK(cudaStreamSynchronize(cs));
   out->n_reads = n;
-  out->offsets = ctx->h_off.as<uint64_t>();
-  out->lengths = ctx->h_len.as<uint64_t>();
-  out->seq = ctx->h_seq.as<uint8_t>();
-  out->qual = ctx->h_qual.as<uint8_t>();
-  out->real_identity = ctx->h_id.as<double>();
+  out->offsets = sl.h_off.as<uint64_t>();
+  out->lengths = sl.h_len.as<uint64_t>();
+  out->seq = sl.h_seq.as<uint8_t>();
+  out->qual = sl.h_qual.as<uint8_t>();
+  out->real_identity = sl.h_id.as<double>();
   out->total_bytes = total;
-  out->total_bases = ctx->last_bases;
+  out->total_bases = sl.bases;
   out->k = ctx->M.k;
   return RR_OK;
 }
 
+static int require_idle(rr_ctx* ctx, const char* who) {
+  if (ctx->n_submitted != ctx->n_collected) return fail(ctx, RR_ERR_ARG, std::string(who) + ": batches submitted with rr_submit are still in flight (rr_collect them first)");
+  return RR_OK;
+}
+
+RR_API int rr_upload(rr_ctx* ctx, uint64_t n, const rr_desc* descs) {
+  if (!ctx) return RR_ERR_ARG;
+  int rc = require_idle(ctx, "rr_upload");
+  if (rc) return rc;
+  rc = prepare(ctx, ctx->slot[0], n, descs);
+  if (rc) return rc;
+  CK(cudaStreamSynchronize(ctx->stream));
+  return RR_OK;
+}
+
+RR_API int rr_run(rr_ctx* ctx) {
+  if (!ctx) return RR_ERR_ARG;
+  int rc = require_idle(ctx, "rr_run");
+  if (rc) return rc;
+  Slot& sl = ctx->slot[0];
+  if (!sl.prepared) return fail(ctx, RR_ERR_ARG, "rr_run: nothing uploaded");
+  CK(cudaSetDevice(ctx->device));
+  rc = enqueue(ctx, sl);
+  if (rc) return rc;
+  return finish(ctx, sl);
+}
+
+RR_API int rr_download(rr_ctx* ctx, rr_batch* out) {
+  if (!ctx || !out) return RR_ERR_ARG;
+  Slot& sl = ctx->slot[0];
+  if (!sl.ran) return fail(ctx, RR_ERR_ARG, "rr_download: no completed rr_run");
+  CK(cudaSetDevice(ctx->device));
+  return fetch(ctx, sl, out);
+}
+
+RR_API int rr_submit(rr_ctx* ctx, uint64_t n, const rr_desc* descs) {
+  if (!ctx) return RR_ERR_ARG;
+  if (ctx->n_submitted - ctx->n_collected >= 2) return fail(ctx, RR_ERR_ARG, "rr_submit: two batches already in flight (rr_collect one first)");
+  Slot& sl = ctx->slot[ctx->n_submitted & 1];
+  int rc = prepare(ctx, sl, n, descs);
+  if (rc) return rc;
+  rc = enqueue(ctx, sl);
+  if (rc) return rc;
+  ctx->n_submitted += 1;
+  return RR_OK;
+}
+
+RR_API int rr_collect(rr_ctx* ctx, rr_batch* out) {
+  if (!ctx || !out) return RR_ERR_ARG;
+  if (ctx->n_submitted == ctx->n_collected) return fail(ctx, RR_ERR_ARG, "rr_collect: nothing submitted");
+  CK(cudaSetDevice(ctx->device));
+  Slot& sl = ctx->slot[ctx->n_collected & 1];
+  ctx->n_collected += 1;
+  int rc = finish(ctx, sl);
+  if (rc) return rc;
+  return fetch(ctx, sl, out);
+}
+
 RR_API int rr_generate(rr_ctx* ctx, uint64_t n, const rr_desc* descs, rr_batch* out) {
-  int rc = rr_upload(ctx, n, descs);
+  if (!ctx) return RR_ERR_ARG;
+  int rc = require_idle(ctx, "rr_generate");
   if (rc) return rc;
-  rc = rr_run(ctx);
+  rc = rr_submit(ctx, n, descs);
   if (rc) return rc;
-  return rr_download(ctx, out);
+  return rr_collect(ctx, out);
 }
 
 // ---- debug / parity hooks ---------------------------------------------------------------------------------------
@@ -692,13 +776,14 @@ RR_API int rr_debug_rng_words(rr_ctx* ctx, uint64_t seed, uint64_t first, uint32
 
 RR_API int rr_debug_fetch(rr_ctx* ctx, uint64_t i, int which, uint8_t* out, uint64_t cap, uint64_t* len) {
   if (!ctx || !out || !len) return RR_ERR_ARG;
-  if (!ctx->ran || i >= ctx->n) return fail(ctx, RR_ERR_ARG, "rr_debug_fetch: no such read");
+  const Slot& sl = ctx->slot[ctx->last_slot];
+  if (!sl.ran || i >= sl.n) return fail(ctx, RR_ERR_ARG, "rr_debug_fetch: no such read");
   CK(cudaSetDevice(ctx->device));
   uint64_t l = 0;
-  const DevBuf& lens = which == 0 ? ctx->d_raw_len : ctx->d_cig_len;
+  const DevBuf& lens = which == 0 ? sl.d_raw_len : sl.d_cig_len;
   CK(cudaMemcpy(&l, lens.as<uint64_t>() + i, 8, cudaMemcpyDeviceToHost));
   if (l > cap) return fail(ctx, RR_ERR_ARG, "rr_debug_fetch: buffer too small");
-  const uint8_t* src = which == 0 ? ctx->d_raw.as<uint8_t>() + ctx->h_raw_off[i] : ctx->d_cig.as<uint8_t>() + ctx->h_out_off[i];
+  const uint8_t* src = which == 0 ? ctx->d_raw.as<uint8_t>() + sl.h_raw_off[i] : ctx->d_cig.as<uint8_t>() + sl.h_out_off[i];
   if (l) CK(cudaMemcpy(out, src, l, cudaMemcpyDeviceToHost));
   *len = l;
   return RR_OK;

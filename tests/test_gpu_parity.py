@@ -357,3 +357,39 @@ def test_whole_simulate_fastq_is_byte_identical(orc):
     assert recs == stats["reads"]
     assert out.decode() == text
     ctx.close()
+
+
+def test_submit_collect_pipeline_matches_sync(orc):
+    """rr_submit / rr_collect (double buffered) returns exactly what rr_generate returns, batch after batch."""
+    import rustyread_b200.capi as capi
+
+    fasta = helpers.random_fasta(orc, [150_000])
+    sim = capi.Simulation(fasta, seed=5, length=(4000, 3500), glitches=(1000, 25, 25))
+    ctx = capi.Context(0)
+    sim.attach(ctx)
+    batches = [sim.feed(300_000 + 50_000 * i) for i in range(4)]
+    want = []
+    for d in batches:
+        b = ctx.generate(d)
+        want.append((b.lengths.copy(), b.offsets.copy(), b.seq[:b.total_bytes].copy(), b.qual[:b.total_bytes].copy(), b.real_identity.copy()))
+    ctx.submit(batches[0])
+    for i in range(4):
+        if i + 1 < 4:
+            ctx.submit(batches[i + 1])
+        b = ctx.collect()
+        w = want[i]
+        assert np.array_equal(b.lengths, w[0]) and np.array_equal(b.real_identity, w[4])
+        for r in range(b.n):
+            o, l = int(b.offsets[r]), int(b.lengths[r])
+            wo = int(w[1][r])
+            assert np.array_equal(b.seq[o:o + l], w[2][wo:wo + l]) and np.array_equal(b.qual[o:o + l], w[3][wo:wo + l])
+    import rustyread_b200 as rr
+    with pytest.raises(rr.RRError):
+        ctx.collect()  # nothing in flight
+    ctx.submit(batches[0])
+    ctx.submit(batches[1])
+    with pytest.raises(rr.RRError):
+        ctx.submit(batches[2])  # two already in flight
+    ctx.collect()
+    ctx.collect()
+    ctx.close()
