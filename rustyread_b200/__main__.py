@@ -1,0 +1,49 @@
+"""`python -m rustyread_b200 simulate ...` — the `rustyread simulate` command line (src/cli/mod.rs:10-28,
+src/cli/simulate.rs:162-239) over the B200 library.  Under torchrun every rank drives its own GPU."""
+import argparse
+import gzip
+import os
+import sys
+
+from . import simulate as sim_mod
+
+
+def main(argv=None):
+    ap = argparse.ArgumentParser(prog="rustyread", description="A long read simulator based on badread idea (B200 hot path)")
+    ap.add_argument("-t", "--threads", type=int, default=None, help="accepted for compatibility; the per-read work runs on the GPU")
+    ap.add_argument("-v", "--verbosity", action="count", default=0)
+    sub = ap.add_subparsers(dest="cmd", required=True)
+    s = sub.add_parser("simulate", help="Generate fake long read")
+    s.add_argument("--reference", required=True)
+    s.add_argument("--output", default=None)
+    s.add_argument("--quantity", required=True)
+    d = sim_mod.FLAG_DEFAULTS
+    for name in ("length", "identity", "error_model", "qscore_model", "start_adapter", "end_adapter", "start_adapter_seq", "end_adapter_seq", "glitches"):
+        s.add_argument("--" + name, default=d[name])
+    s.add_argument("--seed", type=int, default=None)
+    for name in ("junk_reads", "random_reads", "chimera"):
+        s.add_argument("--" + name, type=float, default=d[name])
+    s.add_argument("--small_plasmid_bias", action="store_true")
+    s.add_argument("--number_base_store", default=None)
+    a = ap.parse_args(argv)
+
+    rank, world, local = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("LOCAL_RANK", "0"))
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.init_process_group("gloo")  # shard results travel host to host; the data path itself has no collective
+    raw = open(a.reference, "rb").read()
+    fasta = gzip.decompress(raw) if raw[:2] == b"\x1f\x8b" else raw
+    out = (open(a.output, "wb") if a.output else sys.stdout.buffer) if rank == 0 else None
+    flags = {k: getattr(a, k) for k in d}
+    reads, bases = sim_mod.simulate(fasta, a.quantity, out, dist=dist, rank=rank, world=world, device=local, **flags)
+    if rank == 0 and a.verbosity:
+        print("wrote %d reads, %d bases" % (reads, bases), file=sys.stderr)
+    if dist is not None:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

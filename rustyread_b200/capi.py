@@ -313,6 +313,7 @@ HOST_EXPORTS = {
     "rr_sim_attach": (C.c_int, [C.c_void_p, C.c_void_p]),
     "rr_sim_feed": (C.c_int, [C.c_void_p, C.c_uint64, C.POINTER(C.c_void_p), u64p]),
     "rr_sim_fastq": (C.c_int, [C.c_void_p, C.POINTER(rr_batch), C.c_uint64, C.POINTER(C.c_void_p), u64p, u64p, u64p]),
+    "rr_sim_skip_names": (C.c_int, [C.c_void_p, C.c_uint64]),
     "rr_sim_item_description": (C.c_int, [C.c_void_p, C.c_uint64, C.c_char_p, C.c_uint64]),
     "rr_sim_n_refs": (C.c_uint64, [C.c_void_p]),
     "rr_sim_ref": (C.c_void_p, [C.c_void_p, C.c_uint64, u64p, C.POINTER(C.c_int), f64p, C.POINTER(C.c_char_p)]),
@@ -398,6 +399,9 @@ class Simulation:
         t, n, recs, bases = C.c_void_p(), C.c_uint64(), C.c_uint64(), C.c_uint64()
         self._ck(self.lib.dll.rr_sim_fastq(self.h, C.byref(batch_struct), first, C.byref(t), C.byref(n), C.byref(recs), C.byref(bases)))
         return C.string_at(t.value, n.value), recs.value, bases.value
+
+    def skip_names(self, n_records):
+        self._ck(self.lib.dll.rr_sim_skip_names(self.h, n_records))
 
     def refs(self):
         out = []

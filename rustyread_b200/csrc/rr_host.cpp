@@ -709,6 +709,12 @@ RR_API int rr_sim_item_description(rr_sim* s, uint64_t i, char* out, uint64_t ca
   return RR_OK;
 }
 
+RR_API int rr_sim_skip_names(rr_sim* s, uint64_t n_records) {
+  if (!s) return RR_ERR_ARG;
+  for (uint64_t i = 0; i < 2 * n_records; ++i) s->rng.next_u64();
+  return RR_OK;
+}
+
 RR_API int rr_sim_fastq(rr_sim* s, const rr_batch* b, uint64_t first, const char** text, uint64_t* len, uint64_t* n_records, uint64_t* n_bases) {
   if (!s || !b || !text || !len) return RR_ERR_ARG;
   if (first + b->n_reads > s->items.size()) return sfail(s, RR_ERR_ARG, "rr_sim_fastq: batch does not match the last feed");

@@ -1,0 +1,166 @@
+"""`rustyread simulate` driver over the C ABI: the batch loop of src/simulate/mod.rs:129-215, with the
+`par_bridge().map(generate_read)` stage replaced by the device library and, optionally, sharded over the
+ranks of a torch.distributed job (one process per GPU, no collective on the data path).
+
+Sharding: every rank runs the same seeded serial feeder (it is O(10) draws per read), takes a
+contiguous, length-balanced range of the batch's work items, generates it on its own GPU, and ships the packed
+result to rank 0, which is the only rank that formats FASTQ (read names are drawn from main_rng in write
+order, src/simulate/mod.rs:199-203).  The other ranks skip the same number of name draws so that the next
+batch's feeder stays in step.  The file is byte-identical to the single-GPU (and to the reference
+`--threads 1`) output.
+"""
+import numpy as np
+
+from . import capi
+
+FLAG_DEFAULTS = dict(  # src/cli/simulate.rs:165-238
+    length="15000,13000", identity="85,95,5", error_model="nanopore2020", qscore_model="nanopore2020", seed=None,
+    start_adapter="90,60", end_adapter="50,20", start_adapter_seq="AATGTACTTCGTTCAGTTACGTATTGCT",
+    end_adapter_seq="GCAATACGTAACTGAACGAAGT", junk_reads=1.0, random_reads=1.0, chimera=1.0, glitches="10000,25,25",
+    small_plasmid_bias=False, number_base_store=None,
+)
+
+
+def parse_duo(text):  # cli::simulate::Duo, src/cli/simulate.rs:82-101
+    parts = text.split(",")
+    if len(parts) != 2 or not all(p.isdigit() for p in parts):
+        raise ValueError("can't parse %r as <u64>,<u64>" % text)
+    return tuple(int(p) for p in parts)
+
+
+def parse_trio(text):  # cli::simulate::Trio, src/cli/simulate.rs:103-125
+    parts = text.split(",")
+    if len(parts) != 3 or not all(p.isdigit() for p in parts):
+        raise ValueError("can't parse %r as <u64>,<u64>,<u64>" % text)
+    return tuple(int(p) for p in parts)
+
+
+def shard_bounds(descs, world):
+    """Contiguous split of a batch into `world` ranges with about the same number of bases each."""
+    n = len(descs)
+    if world <= 1 or n == 0:
+        return [0, n] + [n] * max(0, world - 1)
+    w = (descs["end"].astype(np.int64) - descs["start"].astype(np.int64))
+    w = np.where(descs["type"] == capi.RR_REAL, np.abs(w), descs["end"].astype(np.int64))
+    cw = (descs["cend"].astype(np.int64) - descs["cstart"].astype(np.int64))
+    w = w + np.where(descs["has_chimera"] == 1, np.abs(cw), 0) + 64
+    csum = np.cumsum(w)
+    bounds = [0]
+    for r in range(1, world):
+        bounds.append(int(np.searchsorted(csum, csum[-1] * r / world)))
+    bounds.append(n)
+    for i in range(1, len(bounds)):
+        bounds[i] = max(bounds[i], bounds[i - 1])
+    return bounds
+
+
+class DeviceGenerator:
+    """generate_fn backed by the CUDA library: descs -> (offsets, lengths, seq, qual, real_identity)."""
+
+    def __init__(self, sim, device=0):
+        self.ctx = capi.Context(device)
+        sim.attach(self.ctx)
+
+    def __call__(self, descs):
+        if len(descs) == 0:
+            return (np.zeros(1, np.uint64), np.zeros(0, np.uint64), np.zeros(0, np.uint8), np.zeros(0, np.uint8), np.zeros(0, np.float64))
+        b = self.ctx.generate(descs)
+        tb = b.total_bytes
+        return (b.offsets.copy(), b.lengths.copy(), b.seq[:tb].copy(), b.qual[:tb].copy(), b.real_identity.copy())
+
+
+def _send(dist, arrays, dst):
+    import torch
+
+    meta = torch.tensor([len(a) for a in arrays], dtype=torch.int64)
+    dist.send(meta, dst)
+    for a in arrays:
+        if len(a):
+            dist.send(torch.from_numpy(np.ascontiguousarray(a).view(np.uint8).copy()), dst)
+
+
+def _recv(dist, dtypes, src):
+    import torch
+
+    meta = torch.zeros(len(dtypes), dtype=torch.int64)
+    dist.recv(meta, src)
+    out = []
+    for n, dt in zip(meta.tolist(), dtypes):
+        nbytes = n * np.dtype(dt).itemsize
+        t = torch.zeros(nbytes, dtype=torch.uint8)
+        if nbytes:
+            dist.recv(t, src)
+        out.append(t.numpy().view(dt))
+    return out
+
+
+def simulate(fasta, quantity, output, generate_factory=None, dist=None, rank=0, world=1, device=0, **flags):
+    """Run `rustyread simulate`.  `output` is a binary file object (only used on rank 0).  Returns (reads, bases)."""
+    f = dict(FLAG_DEFAULTS)
+    f.update({k: v for k, v in flags.items() if v is not None})
+    if f["seed"] is None:
+        import time
+
+        f["seed"] = int(time.time())  # src/simulate/mod.rs:31-36
+    for name in ("error_model", "qscore_model"):
+        if f[name] == "nanopore2020":
+            raise FileNotFoundError("model 'nanopore2020' lives in an installed badread package (src/cli/simulate.rs:130-159); "
+                                    "pass a model file, 'random' or (qscore) 'ideal'")
+
+    def model_text(v, builtins):
+        if v in builtins:
+            return v
+        import gzip
+
+        raw = open(v, "rb").read()
+        return gzip.decompress(raw) if raw[:2] == b"\x1f\x8b" else raw
+
+    sim = capi.Simulation(fasta, seed=f["seed"], length=parse_duo(f["length"]), identity=parse_trio(f["identity"]),
+                          start_adapter=parse_duo(f["start_adapter"]), end_adapter=parse_duo(f["end_adapter"]),
+                          start_adapter_seq=f["start_adapter_seq"], end_adapter_seq=f["end_adapter_seq"],
+                          junk_reads=f["junk_reads"], random_reads=f["random_reads"], chimera=f["chimera"],
+                          glitches=parse_trio(f["glitches"]), small_plasmid_bias=f["small_plasmid_bias"],
+                          error_model=model_text(f["error_model"], ("random",)), qscore_model=model_text(f["qscore_model"], ("random", "ideal")))
+    gen = (generate_factory or (lambda s: DeviceGenerator(s, device)))(sim)
+    total = sim.quantity(quantity)
+    limit = sim.quantity(f["number_base_store"]) if f["number_base_store"] else total
+    produced, n_reads, n_bases = 0, 0, 0
+    DT = (np.uint64, np.uint64, np.uint8, np.uint8, np.float64)
+    while produced < total:  # src/simulate/mod.rs:153-214
+        base_loop = min(limit, total - produced)
+        produced += base_loop
+        descs = sim.feed(base_loop)
+        bounds = shard_bounds(descs, world)
+        lo, hi = bounds[rank], bounds[rank + 1]
+        mine = gen(descs[lo:hi])
+        if world > 1:
+            import torch
+
+            if rank == 0:
+                shards = [mine] + [_recv(dist, DT, r) for r in range(1, world)]
+            else:
+                _send(dist, mine, 0)
+                shards = None
+        else:
+            shards = [mine]
+        emitted = 0
+        if rank == 0:
+            for r, (off, ln, seq, qual, ident) in enumerate(shards):
+                if len(ln) == 0:
+                    continue
+                b = capi.batch_struct_from_arrays(off, ln, seq if len(seq) else np.zeros(1, np.uint8), qual if len(qual) else np.zeros(1, np.uint8), ident, sim.k)
+                text, recs, bases = sim.fastq(b, first=bounds[r])
+                output.write(text)
+                emitted += recs
+                n_bases += bases
+            n_reads += emitted
+        if world > 1:
+            import torch
+
+            t = torch.tensor([emitted], dtype=torch.int64)
+            dist.broadcast(t, 0)
+            if rank != 0:
+                sim.skip_names(int(t.item()))
+    if rank == 0:
+        output.flush()
+    return n_reads, n_bases

@@ -1,7 +1,11 @@
 """Shared test plumbing: one workload spec -> (oracle workload, device context) fed with the same inputs."""
 import ctypes as C
 
+import os
+
 import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 DEFAULT = dict(
     seed=42,

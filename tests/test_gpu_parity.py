@@ -393,3 +393,20 @@ def test_submit_collect_pipeline_matches_sync(orc):
     ctx.collect()
     ctx.collect()
     ctx.close()
+
+
+def test_cli_simulate_matches_oracle(orc, tmp_path):
+    """`python -m rustyread_b200 simulate` (the drop-in CLI) writes the same file as the oracle's simulate()."""
+    import subprocess
+    import sys
+
+    fasta = helpers.random_fasta(orc, [90_000, 7_000], circular={1})
+    ref = tmp_path / "ref.fasta"
+    ref.write_text(fasta)
+    out = tmp_path / "reads.fastq"
+    cmd = [sys.executable, "-m", "rustyread_b200", "simulate", "--reference", str(ref), "--quantity", "15x", "--seed", "42", "--error_model", "random",
+           "--qscore_model", "random", "--output", str(out), "--number_base_store", "500K", "--chimera", "5"]
+    r = subprocess.run(cmd, capture_output=True, text=True, cwd=helpers.ROOT if hasattr(helpers, "ROOT") else None, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    text, stats = orc.simulate(dict(seed=42, quantity="15x", chimera=5, number_base_store="500K", threads=8), fasta, capture=True)
+    assert out.read_text() == text and stats["reads"] > 50
