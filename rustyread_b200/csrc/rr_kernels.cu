@@ -440,9 +440,9 @@ static int plan(rr_ctx* ctx, Slot& sl) {
 // must not race with kernels of the other slot still in flight: the caller drains the compute stream first when needed.
 static int upload_plan(rr_ctx* ctx, Slot& sl) {
   const uint64_t n = sl.n;
-  uint32_t want_blocks = (uint32_t)std::min<uint64_t>((uint64_t)ctx->n_sm * 4, (n + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK);
+  uint32_t want_blocks = (uint32_t)std::min<uint64_t>((uint64_t)ctx->n_sm * RR_BLOCKS_PER_SM, (n + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK);
   sl.read_grid = std::max<uint32_t>(1, want_blocks);  // persistent grid: 4 blocks of 8 warps per SM, fewer if the batch is small
-  const uint64_t n_warps = (uint64_t)ctx->n_sm * 4 * WARPS_PER_BLOCK;
+  const uint64_t n_warps = (uint64_t)ctx->n_sm * RR_BLOCKS_PER_SM * WARPS_PER_BLOCK;
   const uint64_t grec = std::max(ctx->sc_grec_cap, sl.sc_grec_cap), gseq = std::max(ctx->sc_gseq_cap, sl.sc_gseq_cap);
   const bool grow = sl.h_raw_off[n] + 16 > ctx->d_raw.cap || sl.h_out_off[n] + 16 > ctx->d_err.cap || sl.h_out_off[n] + 16 > ctx->d_cig.cap ||
                     n_warps * ctx->sc_rows_cap * 8 > ctx->d_sc_rows.cap || n_warps * ctx->sc_ops_cap > ctx->d_sc_ops.cap ||

@@ -425,7 +425,7 @@ __device__ __forceinline__ void process_read(const ReadKernelParams& P, WarpSmem
   }
 }
 
-__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, 4) rr_read_kernel(const __grid_constant__ ReadKernelParams P) {
+__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, RR_BLOCKS_PER_SM) rr_read_kernel(const __grid_constant__ ReadKernelParams P) {
   __shared__ WarpSmem smem[WARPS_PER_BLOCK];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t gwarp = blockIdx.x * WARPS_PER_BLOCK + warp;
