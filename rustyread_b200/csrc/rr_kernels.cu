@@ -714,7 +714,7 @@ RR_API int rr_generate(rr_ctx* ctx, uint64_t n, const rr_desc* descs, rr_batch* 
 __global__ void rr_debug_align_kernel(ReadKernelParams P, const uint8_t* q, uint32_t m, const uint8_t* t, uint32_t n, uint8_t* cigar,
                                       uint32_t* out) {
   __shared__ WarpSmem ws;
-  uint64_t a = warp_align(&ws, P, 0, q, m, t, n, cigar, (uint64_t)m + n, threadIdx.x & 31);
+  uint64_t a = warp_align(&ws, P, 0, q, m, t, n, cigar, threadIdx.x & 31);
   if (threadIdx.x == 0) { out[0] = align_nops(a); out[1] = align_edits(a); out[2] = align_status(a); }
 }
 

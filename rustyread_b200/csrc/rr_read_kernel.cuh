@@ -184,22 +184,16 @@ struct Stitch {
   uint32_t status;
 };
 
-__device__ __forceinline__ bool st_reserve(Stitch& S, uint32_t n_err, uint32_t n_cig) {
-  if (S.err_len + n_err > S.cap || S.cig_len + n_cig > S.cap) {
-    S.status = ST_OUT_OVERFLOW;
-    return false;
-  }
-  return true;
-}
-
-__device__ __forceinline__ void st_emit_gap(Stitch& S, uint32_t upto, int lane) {  // raw[pos_in_raw..upto) copied, '=' in the CIGAR
-  if (upto <= S.pos_in_raw) return;
-  uint32_t n = upto - S.pos_in_raw;
-  if (!st_reserve(S, n, n)) return;
+// Capacity is checked once per event by the caller (add_change) or by st_tail.
+__device__ __forceinline__ void st_emit_gap(Stitch& S, uint32_t n, int lane) {  // raw[pos_in_raw .. +n) copied, '=' in the CIGAR
   const uint8_t* src = S.raw + S.pos_in_raw;
   uint8_t* de = S.err + S.err_len;
   uint8_t* dc = S.cig + S.cig_len;
-  for (uint32_t i = lane; i < n; i += 32) {
+  if ((uint32_t)lane < n) {
+    de[lane] = src[lane];
+    dc[lane] = '=';
+  }
+  for (uint32_t i = lane + 32; i < n; i += 32) {
     de[i] = src[i];
     dc[i] = '=';
   }
@@ -208,9 +202,9 @@ __device__ __forceinline__ void st_emit_gap(Stitch& S, uint32_t upto, int lane) 
 }
 
 __device__ __forceinline__ void st_emit_seq(Stitch& S, const uint8_t* q, uint32_t n, int lane) {
-  if (!st_reserve(S, n, 0)) return;
   uint8_t* de = S.err + S.err_len;
-  for (uint32_t i = lane; i < n; i += 32) de[i] = q[i];
+  if ((uint32_t)lane < n) de[lane] = q[lane];
+  for (uint32_t i = lane + 32; i < n; i += 32) de[i] = q[i];
   S.err_len += n;
 }
 
@@ -240,6 +234,7 @@ __device__ __forceinline__ uint32_t add_change(Stitch& S, WarpSmem* ws, const Re
       S.lseq_len += olen - es;
     }
   }
+  uint32_t gap = 0;
   if (!merge) {  // push a new change (update_align: error.rs:155-164)
     if (S.has_last && S.l_emit) {  // the previous change is final: sequence() accounts for it
       S.real_edit += S.ledit;
@@ -254,13 +249,18 @@ __device__ __forceinline__ uint32_t add_change(Stitch& S, WarpSmem* ws, const Re
     S.le = oe;
     S.lseq_len = olen;
     S.ledit = 0;
-    if (S.l_emit) st_emit_gap(S, ob, lane);
+    gap = ob - S.pos_in_raw;  // only meaningful when l_emit
   }
-  const uint32_t add = olen - es;
-  if (S.l_emit) st_emit_seq(S, oseq + es, add, lane);
-  if (S.status) return 0;
-  const uint64_t a = warp_align(ws, P, gwarp, oseq + es, add, S.raw + rs, re - rs,
-                                S.l_emit ? S.cig + S.cig_len : nullptr, S.cap - S.cig_len, lane);
+  const uint32_t add = olen - es, tn = re - rs;
+  uint8_t* dst = nullptr;
+  if (S.l_emit) {
+    // one capacity check per event: the CIGAR of this piece has at most add + tn ops
+    if (S.err_len + gap + add > S.cap || S.cig_len + gap + add + tn > S.cap) { S.status = ST_OUT_OVERFLOW; return 0; }
+    if (gap) st_emit_gap(S, gap, lane);
+    st_emit_seq(S, oseq + es, add, lane);
+    dst = S.cig + S.cig_len;
+  }
+  const uint64_t a = warp_align(ws, P, gwarp, oseq + es, add, S.raw + rs, tn, dst, lane);
   if (align_status(a)) { S.status = align_status(a); return 0; }
   if (S.l_emit) S.cig_len += align_nops(a);
   S.ledit += align_edits(a);
@@ -412,7 +412,11 @@ __device__ __forceinline__ void process_read(const ReadKernelParams& P, WarpSmem
       S.real_edit += S.ledit;
       S.pos_in_raw = S.le;
     }
-    if (S.pos_in_raw < L) st_emit_gap(S, L, lane);
+    if (S.pos_in_raw < L) {
+      const uint32_t n = L - S.pos_in_raw;
+      if (S.err_len + n > S.cap || S.cig_len + n > S.cap) S.status = ST_OUT_OVERFLOW;
+      else st_emit_gap(S, n, lane);
+    }
   }
   __syncwarp();
   if (lane == 0) {
