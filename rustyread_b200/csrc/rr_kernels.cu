@@ -68,7 +68,7 @@ struct rr_ctx {
   DevBuf d_ref, d_ref_off, d_ref_circ;
   DevBuf d_em_index, d_em_alt_begin, d_em_alt_off, d_em_alt_bytes, d_em_cum, d_em_scale;
   DevBuf d_adapter;
-  DevBuf d_q_tab_off, d_q_tab, d_q_dist_off, d_q_scores, d_q_cum, d_q_scale;
+  DevBuf d_q_tab_off, d_q_tab, d_q_dist_off, d_q_scores, d_q_cum, d_q_scale, d_q_unit;
 
   // Up to two batches in flight (rr_submit / rr_collect): per-batch state lives in a slot; the big working
   // arenas (raw / err / cigar) and the per-warp scratch are shared because kernels of consecutive batches are
@@ -164,7 +164,7 @@ RR_API void rr_destroy(rr_ctx* ctx) {
   cudaStreamSynchronize(ctx->copy_stream);
   DevBuf* bufs[] = {&ctx->d_ref, &ctx->d_ref_off, &ctx->d_ref_circ, &ctx->d_em_index, &ctx->d_em_alt_begin, &ctx->d_em_alt_off,
                     &ctx->d_em_alt_bytes, &ctx->d_em_cum, &ctx->d_em_scale, &ctx->d_adapter, &ctx->d_q_tab_off, &ctx->d_q_tab,
-                    &ctx->d_q_dist_off, &ctx->d_q_scores, &ctx->d_q_cum, &ctx->d_q_scale, &ctx->d_raw, &ctx->d_err, &ctx->d_cig,
+                    &ctx->d_q_dist_off, &ctx->d_q_scores, &ctx->d_q_cum, &ctx->d_q_scale, &ctx->d_q_unit, &ctx->d_raw, &ctx->d_err, &ctx->d_cig,
                     &ctx->d_sc_rows, &ctx->d_sc_ops, &ctx->d_sc_grec, &ctx->d_sc_gseq};
   for (auto* b : bufs) b->release();
   for (auto& sl : ctx->slot) {
@@ -281,9 +281,13 @@ RR_API int rr_set_qscore_model(rr_ctx* ctx, uint32_t max_k, uint64_t n, const ui
   const uint32_t n_sc = score_off[n];
   std::vector<double> cum(std::max<uint32_t>(1, n_sc)), scale(n);
   std::vector<char> dist_ok(n, 1);
+  std::vector<uint8_t> unit(n, 0);
   for (uint64_t i = 0; i < n; ++i) {
     uint32_t a0 = score_off[i], a1 = score_off[i + 1];
-    if (a1 <= a0 || !weighted_index_build(weights + a0, a1 - a0, cum.data() + a0, &scale[i])) dist_ok[i] = 0;
+    if (a1 <= a0 || !weighted_index_build(weights + a0, a1 - a0, cum.data() + a0, &scale[i])) { dist_ok[i] = 0; continue; }
+    bool u = (a1 - a0) < (1u << 20);
+    for (uint32_t j = a0; j < a1 && u; ++j) u = weights[j] == 1.0;
+    unit[i] = u ? 1 : 0;  // partial sums are then exactly 1, 2, 3, ... (Quality::random / ideal)
   }
   const uint32_t margin = (max_k - 1) / 2;
   std::vector<uint32_t> tab_off(2 * margin + 2, 0);
@@ -315,7 +319,7 @@ RR_API int rr_set_qscore_model(rr_ctx* ctx, uint32_t max_k, uint64_t n, const ui
   }
   std::vector<uint8_t> sc(scores, scores + n_sc);
   if (!upload(ctx, ctx->d_q_tab_off, tab_off) || !upload(ctx, ctx->d_q_tab, tab) || !upload(ctx, ctx->d_q_dist_off, dist_off) ||
-      !upload(ctx, ctx->d_q_scores, sc) || !upload(ctx, ctx->d_q_cum, cum) || !upload(ctx, ctx->d_q_scale, scale))
+      !upload(ctx, ctx->d_q_scores, sc) || !upload(ctx, ctx->d_q_cum, cum) || !upload(ctx, ctx->d_q_scale, scale) || !upload(ctx, ctx->d_q_unit, unit))
     return fail(ctx, RR_ERR_CUDA, "rr_set_qscore_model: upload failed");
   ctx->Q.max_k = max_k;
   ctx->Q.tab_off = ctx->d_q_tab_off.as<uint32_t>();
@@ -324,6 +328,7 @@ RR_API int rr_set_qscore_model(rr_ctx* ctx, uint32_t max_k, uint64_t n, const ui
   ctx->Q.scores = ctx->d_q_scores.as<uint8_t>();
   ctx->Q.cum = ctx->d_q_cum.as<double>();
   ctx->Q.scale = ctx->d_q_scale.as<double>();
+  ctx->Q.unit = ctx->d_q_unit.as<uint8_t>();
   ctx->have_qscore = true;
   return RR_OK;
 }

@@ -27,6 +27,7 @@ struct QscoreModelDev {
   const uint8_t* scores;
   const double* cum;         // per dist: partial sums, last = total
   const double* scale;       // per dist
+  const uint8_t* unit;       // per dist: 1 when every weight is exactly 1.0 (partial sums are 1, 2, 3, ...)
 };
 
 struct QscoreKernelParams {
@@ -49,7 +50,7 @@ __device__ __forceinline__ uint32_t cigar_sym(uint8_t c) { return c == '=' ? 0u 
 
 __global__ void __launch_bounds__(Q_THREADS) rr_qscore_kernel(const __grid_constant__ QscoreKernelParams P) {
   __shared__ uint32_t s_words[Q_THREADS * 16];
-  __shared__ __align__(8) uint8_t s_cig[Q_HALO + Q_TILE + Q_HALO];
+  __shared__ __align__(16) uint8_t s_cig[Q_HALO + Q_TILE + Q_HALO];
   __shared__ uint32_t s_warp_sum[Q_THREADS / 32];
   __shared__ uint32_t s_slot;
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
@@ -77,9 +78,18 @@ __global__ void __launch_bounds__(Q_THREADS) rr_qscore_kernel(const __grid_const
       const uint32_t tn = (uint32_t)min((uint64_t)Q_TILE, n - t0);
       __syncthreads();
       // stage the tile (+ halo) of the CIGAR
-      for (uint32_t x = tid; x < tn + 2 * Q_HALO; x += Q_THREADS) {
-        int64_t gi = (int64_t)t0 + (int64_t)x - Q_HALO;
-        s_cig[x] = (gi >= 0 && (uint64_t)gi < n) ? cig[gi] : 0;
+      // body: one aligned 8-byte load per thread (read offsets are 16-byte aligned, tiles are multiples of 8)
+      {
+        const uint32_t p8 = tid * 8;
+        if (p8 + 8 <= tn) {
+          *reinterpret_cast<uint2*>(s_cig + Q_HALO + p8) = *reinterpret_cast<const uint2*>(cig + t0 + p8);
+        } else {
+          for (uint32_t x = p8; x < tn; ++x) s_cig[Q_HALO + x] = cig[t0 + x];
+        }
+        if (tid < 2 * Q_HALO) {  // halo: 8 positions before the tile, 8 after
+          const int64_t gi = tid < Q_HALO ? (int64_t)t0 - Q_HALO + tid : (int64_t)t0 + tn + (tid - Q_HALO);
+          s_cig[tid < Q_HALO ? tid : Q_HALO + tn + (tid - Q_HALO)] = (gi >= 0 && (uint64_t)gi < n) ? cig[gi] : 0;
+        }
       }
       __syncthreads();
       // rank the non-'D' positions: 8 consecutive positions per thread
@@ -131,7 +141,8 @@ __global__ void __launch_bounds__(Q_THREADS) rr_qscore_kernel(const __grid_const
         const uint32_t len = 2 * half + 1;
         const uint8_t* wptr = s_cig + Q_HALO + p0 + x - half;
         uint32_t code = 0;
-        for (uint32_t y = 0; y < len; ++y) code |= cigar_sym(wptr[y]) << (2 * y);
+        if (margin == 0) code = cigar_sym(wptr[0]);  // max_k == 1 (Quality::random): the window is the position itself
+        else for (uint32_t y = 0; y < len; ++y) code |= cigar_sym(wptr[y]) << (2 * y);
         const uint32_t dist = Q.tab[Q.tab_off[len] + code];
         uint8_t qv = '!';
         if (dist == 0xFFFFu) {
@@ -142,9 +153,13 @@ __global__ void __launch_bounds__(Q_THREADS) rr_qscore_kernel(const __grid_const
           const uint32_t d0 = Q.dist_off[dist], nd = Q.dist_off[dist + 1] - d0;
           const double chosen = u64_to_unit12(v) * Q.scale[dist] + 0.0;
           uint32_t lo = 0, hi = nd - 1;  // partition_point over the first nd - 1 partial sums
-          while (lo < hi) {
-            uint32_t mid = (lo + hi) >> 1;
-            if (Q.cum[d0 + mid] <= chosen) lo = mid + 1; else hi = mid;
+          if (Q.unit[dist]) {
+            lo = min((uint32_t)chosen, hi);  // partial sums are exactly 1, 2, ..: #{i : i + 1 <= chosen} = floor(chosen)
+          } else {
+            while (lo < hi) {
+              uint32_t mid = (lo + hi) >> 1;
+              if (Q.cum[d0 + mid] <= chosen) lo = mid + 1; else hi = mid;
+            }
           }
           qv = Q.scores[d0 + lo] + 33;
         }

@@ -18,7 +18,7 @@ def norm(s):
     return re.sub(r"\s+", " ", s)
 ncu_ops = [norm(r[isrc]) for r in data]
 # sections
-secs = []; cur = None; name = None; line = None
+secs = []; cur = None; name = None; line = None; KSEL = os.environ.get("KSEL", "")
 for l in dis:
     if l.startswith(".text."):
         name = l[6:].rstrip(":"); cur = []; secs.append((name, cur)); line = None; continue
