@@ -379,6 +379,8 @@ ORC_API void orc_workload_items(void* w_, uint64_t* desc12, double* identity, ui
     length[i] = it.desc.length;
   }
 }
+// test hook: overwrite the target identity of fed item i (edge cases such as 0.0 / 1.0 that Identity never draws)
+ORC_API void orc_workload_set_item_identity(void* w_, uint64_t i, double identity) { ((Workload*)w_)->items[i].desc.identity = identity; }
 // generate_read for every fed item on `threads` CPU threads; returns seconds spent, <0 on failure
 ORC_API double orc_workload_generate(void* w_, int threads, int keep_cigar_raw) {
   Workload* w = (Workload*)w_;

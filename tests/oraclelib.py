@@ -125,6 +125,7 @@ class Oracle:
             "orc_workload_feed": (C.c_uint64, [C.c_void_p, C.c_uint64, C.c_uint64]),
             "orc_workload_items": (None, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
             "orc_workload_generate": (C.c_double, [C.c_void_p, C.c_int, C.c_int]),
+            "orc_workload_set_item_identity": (None, [C.c_void_p, C.c_uint64, C.c_double]),
             "orc_workload_out_len": (C.c_uint64, [C.c_void_p, C.c_uint64, C.c_int]),
             "orc_workload_out_lens": (None, [C.c_void_p, C.c_int, C.c_void_p]),
             "orc_workload_out_copy": (None, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
@@ -274,6 +275,9 @@ class Workload:
         if self.n:
             self.L.orc_workload_items(self.h, d.ctypes.data, ident.ctypes.data, length.ctypes.data)
         return d, ident, length
+
+    def set_item_identity(self, i, identity):
+        self.L.orc_workload_set_item_identity(self.h, i, identity)
 
     def generate(self, threads=1, keep_cigar_raw=True):
         s = self.L.orc_workload_generate(self.h, threads, int(keep_cigar_raw))

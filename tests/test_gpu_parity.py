@@ -410,3 +410,37 @@ def test_cli_simulate_matches_oracle(orc, tmp_path):
     assert r.returncode == 0, r.stderr[-2000:]
     text, stats = orc.simulate(dict(seed=42, quantity="15x", chimera=5, number_base_store="500K", threads=8), fasta, capture=True)
     assert out.read_text() == text and stats["reads"] > 50
+
+
+def test_identity_edge_cases_and_stuck_glitches(orc):
+    """identity 0.0 drives gen_bool with p == 1.0 (no draw consumed, rand Bernoulli ALWAYS_TRUE) until the budget
+    moves off the diagonal; identity 1.0 is a walk with p == 0 at every position; a glitch rate of 2 makes
+    zero-distance glitches (which block all later ones, SURVEY Appendix B #10) the common case."""
+    import rustyread_b200.capi as capi
+
+    fasta = helpers.random_fasta(orc, [60_000])
+    w, ctx, s = helpers.make_pair(orc, fasta, dict(length=(1500.0, 1200.0), glitch=(2.0, 3.0, 3.0), rates=(5.0, 5.0, 20.0)))
+    n = w.feed(300_000)
+    d, ident, _ = w.items()
+    for i in range(n):
+        if i % 3 == 0:
+            ident[i] = 0.0
+        elif i % 3 == 1:
+            ident[i] = 1.0
+        else:
+            ident[i] = 0.5
+        w.set_item_identity(i, float(ident[i]))
+    batch = ctx.generate(capi.descs_from_oracle_items(d, ident))
+    w.generate(threads=8)
+    helpers.compare_batch(w, batch, ctx)
+    assert n > 100
+    ctx.close()
+
+
+def test_multi_contig_genome_scale_layout(orc):
+    """BASELINE config 3 in miniature: 24 linear contigs with human-like relative lengths (3.1 Mbp total), 4x."""
+    rel = [248, 242, 198, 190, 181, 171, 159, 145, 138, 133, 135, 133, 114, 107, 102, 90, 83, 80, 58, 64, 46, 50, 156, 57]
+    fasta = helpers.random_fasta(orc, [r * 1000 for r in rel])
+    _, ctx, batch, n = _run_pair(orc, fasta, {}, 12_000_000)
+    assert n > 500
+    ctx.close()
