@@ -67,6 +67,11 @@ int rr_sim_feed(rr_sim* s, uint64_t base_loop, const rr_desc** descs, uint64_t* 
 int rr_sim_fastq(rr_sim* s, const rr_batch* batch, uint64_t first, const char** text, uint64_t* len,
                  uint64_t* n_records, uint64_t* n_bases);
 
+/* The same records written straight to file descriptor `fd` with writev(2): headers come from a small scratch
+ * buffer, sequence and quality bytes are sent from the batch's (pinned) arenas without an intermediate copy. */
+int rr_sim_write_fastq(rr_sim* s, const rr_batch* batch, uint64_t first, int fd, uint64_t* n_records, uint64_t* n_bases,
+                       uint64_t* n_bytes);
+
 /* Advance main_rng past the read-name draws of `n_records` emitted reads (2 u64 each, mod.rs:201) without
  * formatting anything: what the ranks that do not write the file call to stay in step with the writer rank. */
 int rr_sim_skip_names(rr_sim* s, uint64_t n_records);

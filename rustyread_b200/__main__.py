@@ -37,7 +37,8 @@ def main(argv=None):
     fasta = gzip.decompress(raw) if raw[:2] == b"\x1f\x8b" else raw
     out = (open(a.output, "wb") if a.output else sys.stdout.buffer) if rank == 0 else None
     flags = {k: getattr(a, k) for k in d}
-    reads, bases = sim_mod.simulate(fasta, a.quantity, out, dist=dist, rank=rank, world=world, device=local, **flags)
+    chunk = int(os.environ.get("RUSTYREAD_B200_CHUNK_BASES", "1000000000"))  # device chunk size inside one reference batch
+    reads, bases = sim_mod.simulate(fasta, a.quantity, out, dist=dist, rank=rank, world=world, device=local, chunk_bases=chunk, **flags)
     if rank == 0 and a.verbosity:
         print("wrote %d reads, %d bases" % (reads, bases), file=sys.stderr)
     if dist is not None:

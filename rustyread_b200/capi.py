@@ -313,6 +313,7 @@ HOST_EXPORTS = {
     "rr_sim_attach": (C.c_int, [C.c_void_p, C.c_void_p]),
     "rr_sim_feed": (C.c_int, [C.c_void_p, C.c_uint64, C.POINTER(C.c_void_p), u64p]),
     "rr_sim_fastq": (C.c_int, [C.c_void_p, C.POINTER(rr_batch), C.c_uint64, C.POINTER(C.c_void_p), u64p, u64p, u64p]),
+    "rr_sim_write_fastq": (C.c_int, [C.c_void_p, C.POINTER(rr_batch), C.c_uint64, C.c_int, u64p, u64p, u64p]),
     "rr_sim_skip_names": (C.c_int, [C.c_void_p, C.c_uint64]),
     "rr_sim_item_description": (C.c_int, [C.c_void_p, C.c_uint64, C.c_char_p, C.c_uint64]),
     "rr_sim_n_refs": (C.c_uint64, [C.c_void_p]),
@@ -399,6 +400,12 @@ class Simulation:
         t, n, recs, bases = C.c_void_p(), C.c_uint64(), C.c_uint64(), C.c_uint64()
         self._ck(self.lib.dll.rr_sim_fastq(self.h, C.byref(batch_struct), first, C.byref(t), C.byref(n), C.byref(recs), C.byref(bases)))
         return C.string_at(t.value, n.value), recs.value, bases.value
+
+    def write_fastq(self, batch_struct, fd, first=0):
+        """Write the records of a device batch to file descriptor fd (writev straight from the pinned arenas)."""
+        recs, bases, nbytes = C.c_uint64(), C.c_uint64(), C.c_uint64()
+        self._ck(self.lib.dll.rr_sim_write_fastq(self.h, C.byref(batch_struct), first, fd, C.byref(recs), C.byref(bases), C.byref(nbytes)))
+        return recs.value, bases.value, nbytes.value
 
     def skip_names(self, n_records):
         self._ck(self.lib.dll.rr_sim_skip_names(self.h, n_records))

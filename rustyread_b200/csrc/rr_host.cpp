@@ -17,6 +17,10 @@
 #include <unordered_map>
 #include <vector>
 
+#include <cerrno>
+#include <sys/uio.h>
+#include <unistd.h>
+
 #include "../../include/rustyread_b200_host.h"
 #include "rr_rng.cuh"
 
@@ -706,6 +710,79 @@ RR_API int rr_sim_item_description(rr_sim* s, uint64_t i, char* out, uint64_t ca
   append_description(s, t, d, 0, d.identity);
   if (t.size() + 1 > cap) return RR_ERR_ARG;
   std::memcpy(out, t.c_str(), t.size() + 1);
+  return RR_OK;
+}
+
+RR_API int rr_sim_write_fastq(rr_sim* s, const rr_batch* b, uint64_t first, int fd, uint64_t* n_records, uint64_t* n_bases, uint64_t* n_bytes) {
+  if (!s || !b) return RR_ERR_ARG;
+  if (first + b->n_reads > s->items.size()) return sfail(s, RR_ERR_ARG, "rr_sim_write_fastq: batch does not match the last feed");
+  const uint32_t k = b->k;
+  // headers for a block of records are laid out in one string; iovecs point into it and into the batch arenas
+  constexpr size_t BLOCK = 200;  // records per writev (5 iovecs each, IOV_MAX is 1024)
+  std::string& hdr = s->fastq;
+  std::vector<iovec> iov;
+  std::vector<size_t> hoff;  // per record: offset of "@uuid comment\n" and of "\n+ comment\n" in hdr
+  uint64_t recs = 0, bases = 0, bytes = 0;
+  static const char NL = '\n';
+  std::string comment;
+  uint64_t i = 0;
+  while (i < b->n_reads) {
+    hdr.clear();
+    hoff.clear();
+    std::vector<uint64_t> idx;
+    for (; i < b->n_reads && idx.size() < BLOCK; ++i) {
+      const uint64_t l = b->lengths[i];
+      if (l <= 14) continue;  // mod.rs:192-194
+      if (l < 2ULL * k) return sfail(s, RR_ERR_READ, "rr_sim_write_fastq: read shorter than 2k (the reference panics slicing it)");
+      uint64_t lo = s->rng.next_u64(), hi = s->rng.next_u64();
+      uint8_t name[16];
+      for (int x = 0; x < 8; ++x) { name[x] = (uint8_t)(hi >> (56 - 8 * x)); name[8 + x] = (uint8_t)(lo >> (56 - 8 * x)); }
+      comment.clear();
+      append_description(s, comment, s->items[first + i], l, b->real_identity[i]);
+      hoff.push_back(hdr.size());
+      hdr += '@';
+      uuid_v3_x500(name, hdr);
+      hdr += ' ';
+      hdr += comment;
+      hdr += '\n';
+      hoff.push_back(hdr.size());
+      hdr += "\n+ ";
+      hdr += comment;
+      hdr += '\n';
+      hoff.push_back(hdr.size());
+      idx.push_back(i);
+    }
+    iov.clear();
+    for (size_t r = 0; r < idx.size(); ++r) {
+      const uint64_t j = idx[r], n = b->lengths[j] - 2ULL * k;
+      const char* h = hdr.data();
+      iov.push_back({(void*)(h + hoff[3 * r]), hoff[3 * r + 1] - hoff[3 * r]});
+      iov.push_back({(void*)(b->seq + b->offsets[j] + k), (size_t)n});
+      iov.push_back({(void*)(h + hoff[3 * r + 1]), hoff[3 * r + 2] - hoff[3 * r + 1]});
+      iov.push_back({(void*)(b->qual + b->offsets[j] + k), (size_t)n});
+      iov.push_back({(void*)&NL, 1});
+      ++recs;
+      bases += n;
+    }
+    size_t at = 0;
+    while (at < iov.size()) {  // writev may write less than asked
+      ssize_t w = ::writev(fd, iov.data() + at, (int)std::min<size_t>(iov.size() - at, 1000));
+      if (w < 0) {
+        if (errno == EINTR) continue;
+        return sfail(s, RR_ERR_ARG, std::string("rr_sim_write_fastq: writev failed: ") + std::strerror(errno));
+      }
+      bytes += (uint64_t)w;
+      size_t left = (size_t)w;
+      while (left > 0 && at < iov.size()) {
+        if (left >= iov[at].iov_len) { left -= iov[at].iov_len; ++at; }
+        else { iov[at].iov_base = (char*)iov[at].iov_base + left; iov[at].iov_len -= left; left = 0; }
+      }
+      while (at < iov.size() && iov[at].iov_len == 0) ++at;
+    }
+  }
+  if (n_records) *n_records = recs;
+  if (n_bases) *n_bases = bases;
+  if (n_bytes) *n_bytes = bytes;
   return RR_OK;
 }
 

@@ -94,7 +94,55 @@ def _recv(dist, dtypes, src):
     return out
 
 
-def simulate(fasta, quantity, output, generate_factory=None, dist=None, rank=0, world=1, device=0, **flags):
+def chunk_bounds(descs, chunk_bases):
+    """Split a batch into contiguous device chunks of about `chunk_bases` bases (whole batch if it is smaller)."""
+    n = len(descs)
+    if n == 0:
+        return [0, 0]
+    w = np.where(descs["type"] == capi.RR_REAL, np.abs(descs["end"].astype(np.int64) - descs["start"].astype(np.int64)), descs["end"].astype(np.int64)) + 64
+    csum = np.cumsum(w)
+    k = max(1, int(round(csum[-1] / max(1, chunk_bases))))
+    bounds = [0] + [int(np.searchsorted(csum, csum[-1] * i / k)) for i in range(1, k)] + [n]
+    return sorted(set(bounds))
+
+
+def _simulate_single_gpu(sim, total, limit, output, device, chunk_bases):
+    """One GPU, pipelined: while chunk c is drained and written (writev from pinned memory), chunk c+1 is generated.
+    Chunks are sub-ranges of ONE reference batch, so main_rng sees exactly the reference's order: all Fragments draws
+    of the batch, then one u128 per emitted read in canonical order (src/simulate/mod.rs:163-203)."""
+    ctx = capi.Context(device)
+    sim.attach(ctx)
+    try:
+        fd = output.fileno()
+        output.flush()
+    except Exception:
+        fd = None
+    produced, n_reads, n_bases = 0, 0, 0
+    while produced < total:
+        base_loop = min(limit, total - produced)
+        produced += base_loop
+        descs = sim.feed(base_loop)
+        cb = chunk_bounds(descs, chunk_bases)
+        nchunks = len(cb) - 1
+        if nchunks <= 0:
+            continue
+        ctx.submit(descs[cb[0]:cb[1]])
+        for c in range(nchunks):
+            if c + 1 < nchunks:
+                ctx.submit(descs[cb[c + 1]:cb[c + 2]])
+            b = ctx.collect()
+            if fd is not None:
+                recs, bases, _ = sim.write_fastq(b.struct, fd, first=cb[c])
+            else:
+                text, recs, bases = sim.fastq(b.struct, first=cb[c])
+                output.write(text)
+            n_reads += recs
+            n_bases += bases
+    ctx.close()
+    return n_reads, n_bases
+
+
+def simulate(fasta, quantity, output, generate_factory=None, dist=None, rank=0, world=1, device=0, chunk_bases=1_000_000_000, **flags):
     """Run `rustyread simulate`.  `output` is a binary file object (only used on rank 0).  Returns (reads, bases)."""
     f = dict(FLAG_DEFAULTS)
     f.update({k: v for k, v in flags.items() if v is not None})
@@ -121,9 +169,11 @@ def simulate(fasta, quantity, output, generate_factory=None, dist=None, rank=0, 
                           junk_reads=f["junk_reads"], random_reads=f["random_reads"], chimera=f["chimera"],
                           glitches=parse_trio(f["glitches"]), small_plasmid_bias=f["small_plasmid_bias"],
                           error_model=model_text(f["error_model"], ("random",)), qscore_model=model_text(f["qscore_model"], ("random", "ideal")))
-    gen = (generate_factory or (lambda s: DeviceGenerator(s, device)))(sim)
     total = sim.quantity(quantity)
     limit = sim.quantity(f["number_base_store"]) if f["number_base_store"] else total
+    if world == 1 and generate_factory is None:
+        return _simulate_single_gpu(sim, total, limit, output, device, chunk_bases)
+    gen = (generate_factory or (lambda s: DeviceGenerator(s, device)))(sim)
     produced, n_reads, n_bases = 0, 0, 0
     DT = (np.uint64, np.uint64, np.uint8, np.uint8, np.float64)
     while produced < total:  # src/simulate/mod.rs:153-214

@@ -444,3 +444,18 @@ def test_multi_contig_genome_scale_layout(orc):
     _, ctx, batch, n = _run_pair(orc, fasta, {}, 12_000_000)
     assert n > 500
     ctx.close()
+
+
+def test_pipelined_chunks_and_writev_writer(orc, tmp_path):
+    """simulate() on one GPU: a reference batch split into several device chunks (double buffered), records written
+    with writev straight from pinned memory; the file must equal the oracle's simulate() text."""
+    from rustyread_b200 import simulate as S
+
+    fasta = helpers.random_fasta(orc, [120_000, 9_000], circular={1})
+    out = tmp_path / "reads.fastq"
+    with open(out, "wb") as f:
+        reads, bases = S.simulate(fasta, "20x", f, seed=3, error_model="random", qscore_model="ideal", chimera=8.0, glitches="700,20,20",
+                                  number_base_store="1200K", chunk_bases=150_000)
+    text, stats = orc.simulate(dict(seed=3, quantity="20x", chimera=8, glitches="700,20,20", number_base_store="1200K", threads=8, qscore_model="ideal"), fasta, capture=True)
+    assert (reads, bases) == (stats["reads"], stats["bases"])
+    assert out.read_text() == text
