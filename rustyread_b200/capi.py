@@ -56,6 +56,7 @@ EXPORTS = {
     "rr_stream": (C.c_void_p, [C.c_void_p]),
     "rr_debug_align": (C.c_int, [C.c_void_p, C.c_char_p, C.c_uint32, C.c_char_p, C.c_uint32, C.c_void_p, u32p, u32p]),
     "rr_debug_rng_words": (C.c_int, [C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint32, C.c_void_p]),
+    "rr_debug_set_slack": (C.c_int, [C.c_void_p, C.c_double, u64p]),
     "rr_debug_fetch": (C.c_int, [C.c_void_p, C.c_uint64, C.c_int, C.c_void_p, C.c_uint64, u64p]),
 }
 
@@ -258,6 +259,11 @@ class Context:
         out = np.zeros(n, dtype=np.uint32)
         self._ck(self.lib.dll.rr_debug_rng_words(self.h, seed, first, n, out.ctypes.data))
         return out
+
+    def debug_set_slack(self, slack=0.0):
+        n = C.c_uint64()
+        self._ck(self.lib.dll.rr_debug_set_slack(self.h, slack, C.byref(n)))
+        return n.value
 
     def debug_fetch(self, i, which, cap=1 << 22):
         out = (C.c_uint8 * cap)()

@@ -95,6 +95,8 @@ struct rr_ctx {
   uint64_t n_submitted = 0, n_collected = 0;
   int last_slot = 0;  // slot of the most recently completed run (debug fetch, timings)
   cudaStream_t copy_stream = nullptr;
+  double initial_slack = 1.5;  // capacity planning slack (rr_debug_set_slack)
+  uint64_t n_replans = 0;      // how many times a batch had to be re-planned with more slack
   DevBuf d_raw, d_err, d_cig;
   DevBuf d_sc_rows, d_sc_ops, d_sc_grec, d_sc_gseq;
   uint64_t sc_rows_cap = 32768, sc_ops_cap = 8192, sc_grec_cap = 0, sc_gseq_cap = 0;
@@ -484,7 +486,7 @@ static int prepare(rr_ctx* ctx, Slot& sl, uint64_t n, const rr_desc* descs) {
   sl.prepared = sl.enqueued = sl.ran = false;
   sl.n = n;
   sl.descs.assign(descs, descs + n);
-  sl.slack = 1.5;
+  sl.slack = ctx->initial_slack;
   int rc = plan(ctx, sl);
   if (rc) return rc;
   ENSURE(sl.d_descs, n * sizeof(rr_desc));
@@ -578,7 +580,7 @@ static int enqueue(rr_ctx* ctx, Slot& sl) {
 
 // wait for the batch; on a capacity overflow re-plan with more slack and run again (synchronously)
 static int finish(rr_ctx* ctx, Slot& sl) {
-  for (int attempt = 0; attempt < 6; ++attempt) {
+  for (int attempt = 0; attempt < 12; ++attempt) {
     CK(cudaEventSynchronize(sl.done));
     float a = 0, b = 0, c = 0, w = 0;
     cudaEventElapsedTime(&w, sl.ev[0], sl.ev[3]);
@@ -608,6 +610,7 @@ static int finish(rr_ctx* ctx, Slot& sl) {
       return RR_OK;
     }
     sl.slack *= 2.0;  // capacity estimate too small for `grow` reads
+    ctx->n_replans += 1;
     int rc = plan(ctx, sl);
     if (rc) return rc;
     rc = upload_plan(ctx, sl);
@@ -616,7 +619,7 @@ static int finish(rr_ctx* ctx, Slot& sl) {
     if (rc) return rc;
   }
   sl.enqueued = false;
-  return fail(ctx, RR_ERR_READ, "rr_run: output capacity still too small after 6 attempts");
+  return fail(ctx, RR_ERR_READ, "rr_run: output capacity still too small after 12 attempts");
 }
 
 // D2H of the packed result on the copy stream (the batch's kernels are known to be complete)
@@ -776,6 +779,13 @@ RR_API int rr_debug_rng_words(rr_ctx* ctx, uint64_t seed, uint64_t first, uint32
   CK(cudaMemcpyAsync(out, d.p, (size_t)n * 4, cudaMemcpyDeviceToHost, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
   d.release();
+  return RR_OK;
+}
+
+RR_API int rr_debug_set_slack(rr_ctx* ctx, double slack, uint64_t* replans_so_far) {
+  if (!ctx) return RR_ERR_ARG;
+  if (slack > 0.0) ctx->initial_slack = slack;
+  if (replans_so_far) *replans_so_far = ctx->n_replans;
   return RR_OK;
 }
 

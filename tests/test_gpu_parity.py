@@ -459,3 +459,20 @@ def test_pipelined_chunks_and_writev_writer(orc, tmp_path):
     text, stats = orc.simulate(dict(seed=3, quantity="20x", chimera=8, glitches="700,20,20", number_base_store="1200K", threads=8, qscore_model="ideal"), fasta, capture=True)
     assert (reads, bases) == (stats["reads"], stats["bases"])
     assert out.read_text() == text
+
+
+def test_capacity_overflow_is_replanned_not_truncated(orc):
+    """With an absurdly small planning slack the first attempts overflow (output and glitch scratch); the library must
+    re-plan with more slack until everything fits and still return the exact bytes."""
+    import rustyread_b200.capi as capi
+
+    fasta = helpers.random_fasta(orc, [80_000])
+    w, ctx, s = helpers.make_pair(orc, fasta, dict(length=(3000.0, 2500.0), glitch=(40.0, 30.0, 5.0), identity=(70.0, 90.0, 10.0)))
+    ctx.debug_set_slack(0.01)
+    n = w.feed(600_000)
+    d, ident, _ = w.items()
+    batch = ctx.generate(capi.descs_from_oracle_items(d, ident))
+    assert ctx.debug_set_slack() >= 1  # at least one re-plan happened
+    w.generate(threads=8)
+    helpers.compare_batch(w, batch, ctx)
+    ctx.close()
