@@ -15,8 +15,10 @@
 
 #if defined(__CUDACC__)
 #define RR_HD __host__ __device__ __forceinline__
+#define RR_UNROLL _Pragma("unroll")
 #else
 #define RR_HD inline
+#define RR_UNROLL
 #endif
 
 namespace rr {
@@ -32,7 +34,7 @@ RR_HD uint32_t rotl(uint32_t x, int r) {
 // SeedableRng::seed_from_u64: eight PCG32 outputs form the ChaCha key.
 RR_HD void chacha_key_from_u64(uint64_t state, uint32_t key[8]) {
   const uint64_t MUL = 6364136223846793005ULL, INC = 11634580027462260723ULL;
-#pragma unroll
+  RR_UNROLL
   for (int i = 0; i < 8; ++i) {
     state = state * MUL + INC;
     uint32_t xs = (uint32_t)(((state >> 18) ^ state) >> 27);
@@ -54,7 +56,7 @@ RR_HD void chacha12_block(const uint32_t key[8], uint64_t counter, uint32_t out[
   uint32_t x4 = key[0], x5 = key[1], x6 = key[2], x7 = key[3];
   uint32_t x8 = key[4], x9 = key[5], x10 = key[6], x11 = key[7];
   uint32_t x12 = (uint32_t)counter, x13 = (uint32_t)(counter >> 32), x14 = 0, x15 = 0;
-#pragma unroll
+  RR_UNROLL
   for (int r = 0; r < 6; ++r) {
     RR_QR(x0, x4, x8, x12) RR_QR(x1, x5, x9, x13) RR_QR(x2, x6, x10, x14) RR_QR(x3, x7, x11, x15)
     RR_QR(x0, x5, x10, x15) RR_QR(x1, x6, x11, x12) RR_QR(x2, x7, x8, x13) RR_QR(x3, x4, x9, x14)
