@@ -179,13 +179,18 @@ def main():
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; rustyread_b200 has no CPU fallback")
-    rr.build_library()  # no-op when the in-tree .so is current
     torch.cuda.set_device(local_rank)
     dist = None
     if world > 1:
         import torch.distributed as dist
 
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    # the in-tree .so normally travels with the repo; if it is missing, rank 0 alone compiles it (no CPU fallback exists)
+    from rustyread_b200 import _build
+    if rank == 0 and not os.path.exists(_build.LIB):
+        rr.build_library(force=True)
+    if dist is not None:
+        dist.barrier()
 
     def barrier():
         if dist is not None:
