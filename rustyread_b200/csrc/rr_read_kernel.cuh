@@ -24,6 +24,32 @@ __device__ __forceinline__ uint8_t complement(uint8_t c) {
   }
 }
 
+// Warp copy of a forward-strand reference slice: after a byte-wise head that brings dst to a 16-byte boundary, every
+// lane stores one 128-bit word per step, built from three aligned 64-bit loads of the (differently aligned) source with
+// funnel shifts; the warp moves 512 contiguous bytes per step.  The source may be read up to 15 bytes past src + n
+// (the reference arena is allocated with slack).
+__device__ __forceinline__ void warp_copy_vec(uint8_t* dst, const uint8_t* src, uint64_t n, int lane) {
+  const uint64_t head = min(n, (uint64_t)((16u - (uint32_t)((uintptr_t)dst & 15u)) & 15u));
+  if ((uint64_t)lane < head) dst[lane] = src[lane];
+  const uint64_t nvec = (n - head) >> 4;
+  const uint8_t* sb = src + head;
+  const uint32_t sh = (uint32_t)((uintptr_t)sb & 7u) * 8u;
+  const uint64_t* sa = reinterpret_cast<const uint64_t*>(sb - (sh >> 3));
+  uint4* da = reinterpret_cast<uint4*>(dst + head);
+  for (uint64_t v = lane; v < nvec; v += 32) {
+    const uint64_t a = sa[2 * v], b = sa[2 * v + 1];
+    uint64_t o0 = a, o1 = b;
+    if (sh) {
+      const uint64_t c = sa[2 * v + 2];
+      o0 = (a >> sh) | (b << (64u - sh));
+      o1 = (b >> sh) | (c << (64u - sh));
+    }
+    da[v] = make_uint4((uint32_t)o0, (uint32_t)(o0 >> 32), (uint32_t)o1, (uint32_t)(o1 >> 32));
+  }
+  const uint64_t done = head + (nvec << 4);
+  if (done + (uint64_t)lane < n) dst[done + lane] = src[done + lane];  // tail: fewer than 16 bytes
+}
+
 // Adapter::get_start / get_end (src/model/adapter.rs:64-93): Bernoulli(rate), then a Beta-distributed
 // prefix of the adapter.  Returns the number of bytes appended.
 __device__ __forceinline__ uint32_t add_adapter(WarpRng& rng, const DeviceModels& M, bool end_side, uint8_t* dst, int lane) {
@@ -65,8 +91,8 @@ __device__ __forceinline__ uint64_t add_fragment(WarpRng& rng, const DeviceModel
   else if (M.ref_circ[ref_idx]) { n1 = rl - start; n2 = end; }
   else return 0;
   if (!rc) {
-    for (uint64_t i = lane; i < n1; i += 32) dst[i] = ref[start + i];
-    for (uint64_t i = lane; i < n2; i += 32) dst[n1 + i] = ref[i];
+    warp_copy_vec(dst, ref + start, n1, lane);
+    if (n2) warp_copy_vec(dst + n1, ref, n2, lane);
   } else {
     for (uint64_t i = lane; i < n1; i += 32) dst[i] = complement(ref[rl - 1 - (start + i)]);
     for (uint64_t i = lane; i < n2; i += 32) dst[n1 + i] = complement(ref[rl - 1 - i]);
