@@ -379,6 +379,25 @@ ORC_API void orc_workload_items(void* w_, uint64_t* desc12, double* identity, ui
     length[i] = it.desc.length;
   }
 }
+// inverse of orc_workload_items: replace the fed items by caller-supplied descriptors (same 12-u64 layout), so that a
+// test can run generate_read of the oracle on work items produced elsewhere (e.g. by the product's own feeder)
+ORC_API void orc_workload_load_items(void* w_, const uint64_t* desc12, const double* identity, uint64_t n) {
+  Workload* w = (Workload*)w_;
+  w->items.assign(n, WorkItem());
+  w->outs.clear();
+  auto cs = [](uint64_t s) -> char { return s == 0 ? '+' : (s == 1 ? '-' : '*'); };
+  for (uint64_t i = 0; i < n; ++i) {
+    const uint64_t* d = desc12 + 12 * i;
+    WorkItem& it = w->items[i];
+    it.desc.origin.read_type = (ReadType)d[0]; it.ref_idx = d[1]; it.desc.origin.strand = cs(d[2]); it.desc.origin.start = d[3]; it.desc.origin.end = d[4];
+    if (d[0] == REAL) it.desc.origin.ref_id = w->refs.sequences[d[1]].id;
+    it.desc.has_chimera = d[5] != 0;
+    it.desc.chimera.read_type = (ReadType)d[6]; it.ref_idx2 = d[7]; it.desc.chimera.strand = cs(d[8]); it.desc.chimera.start = d[9]; it.desc.chimera.end = d[10];
+    if (it.desc.has_chimera && d[6] == REAL) it.desc.chimera.ref_id = w->refs.sequences[d[7]].id;
+    it.seed = d[11];
+    it.desc.identity = identity[i];
+  }
+}
 // test hook: overwrite the target identity of fed item i (edge cases such as 0.0 / 1.0 that Identity never draws)
 ORC_API void orc_workload_set_item_identity(void* w_, uint64_t i, double identity) { ((Workload*)w_)->items[i].desc.identity = identity; }
 // generate_read for every fed item on `threads` CPU threads; returns seconds spent, <0 on failure

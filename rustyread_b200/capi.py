@@ -272,6 +272,14 @@ class Context:
         return bytes(out[:n.value])
 
 
+def descs_to_item_table(descs):
+    """rr_desc records -> the (n,12) u64 table + identities used by the oracle's test hooks (test helper)."""
+    d12 = np.zeros((len(descs), 12), dtype=np.uint64)
+    for j, f in enumerate(("type", "ref_idx", "strand", "start", "end", "has_chimera", "ctype", "cref_idx", "cstrand", "cstart", "cend", "seed")):
+        d12[:, j] = descs[f]
+    return d12, np.ascontiguousarray(descs["identity"], dtype=np.float64)
+
+
 def descs_from_oracle_items(d12, identity):
     """Convert the oracle feeder's (n,12) u64 item table into rr_desc records (test helper)."""
     n = len(d12)

@@ -125,6 +125,7 @@ class Oracle:
             "orc_workload_feed": (C.c_uint64, [C.c_void_p, C.c_uint64, C.c_uint64]),
             "orc_workload_items": (None, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
             "orc_workload_generate": (C.c_double, [C.c_void_p, C.c_int, C.c_int]),
+            "orc_workload_load_items": (None, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64]),
             "orc_workload_set_item_identity": (None, [C.c_void_p, C.c_uint64, C.c_double]),
             "orc_workload_out_len": (C.c_uint64, [C.c_void_p, C.c_uint64, C.c_int]),
             "orc_workload_out_lens": (None, [C.c_void_p, C.c_int, C.c_void_p]),
@@ -275,6 +276,13 @@ class Workload:
         if self.n:
             self.L.orc_workload_items(self.h, d.ctypes.data, ident.ctypes.data, length.ctypes.data)
         return d, ident, length
+
+    def load_items(self, d12, identity):
+        """Replace the fed items by caller-supplied descriptors ((n,12) u64 table + identities)."""
+        d12 = np.ascontiguousarray(d12, dtype=np.uint64)
+        identity = np.ascontiguousarray(identity, dtype=np.float64)
+        self.n = len(d12)
+        self.L.orc_workload_load_items(self.h, d12.ctypes.data, identity.ctypes.data, self.n)
 
     def set_item_identity(self, i, identity):
         self.L.orc_workload_set_item_identity(self.h, i, identity)

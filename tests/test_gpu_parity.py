@@ -476,3 +476,23 @@ def test_capacity_overflow_is_replanned_not_truncated(orc):
     w.generate(threads=8)
     helpers.compare_batch(w, batch, ctx)
     ctx.close()
+
+
+def test_two_gpu_cli_matches_oracle(orc, rr, tmp_path):
+    """torchrun with 2 ranks (one process per GPU): sharded generation, single-writer FASTQ == the oracle's simulate()."""
+    import subprocess
+    import sys
+
+    if rr.load_library().device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    fasta = helpers.random_fasta(orc, [150_000, 8_000], circular={1})
+    ref = tmp_path / "ref.fasta"
+    ref.write_text(fasta)
+    out = tmp_path / "reads.fastq"
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1", "--master-port", "29541",
+           "-m", "rustyread_b200", "simulate", "--reference", str(ref), "--quantity", "12x", "--seed", "21", "--error_model", "random",
+           "--qscore_model", "random", "--output", str(out), "--number_base_store", "700K"]
+    r = subprocess.run(cmd, capture_output=True, text=True, cwd=helpers.ROOT, timeout=900)
+    assert r.returncode == 0, r.stderr[-3000:]
+    text, stats = orc.simulate(dict(seed=21, quantity="12x", number_base_store="700K", threads=8), fasta, capture=True)
+    assert out.read_text() == text and stats["reads"] > 50

@@ -15,7 +15,7 @@ import helpers
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 WORKER = textwrap.dedent('''
-    import os, sys
+    import io, os, sys
     sys.path.insert(0, %(root)r); sys.path.insert(0, os.path.join(%(root)r, "tests"))
     import numpy as np
     import torch.distributed as dist
@@ -28,72 +28,25 @@ WORKER = textwrap.dedent('''
     orc = oraclelib.load()
     fasta = open(%(fasta)r, "rb").read()
 
-    class OracleGenerator:  # test stand-in for the device: same interface as simulate.DeviceGenerator
+    class OracleGenerator:
+        """Stand-in for simulate.DeviceGenerator: generate_read of the CPU oracle on the work items it is given."""
         def __init__(self, sim):
-            spec = dict(seed=9, length=(2500.0, 2200.0), rates=(5.0, 5.0, 10.0), glitch=(900.0, 25.0, 25.0))
-            self.w, _ = None, None
-            s = dict(helpers.DEFAULT); s.update(spec)
-            w = orc.workload(s["seed"]); w.set_length(*s["length"]); w.set_references(fasta, adjusted=True)
-            w.set_identity(*s["identity"]); w.set_adapter(*s["adapter"]); w.set_glitch(*s["glitch"]); w.set_error_model(None)
-            w.set_qscore_model("random"); w.set_rates(*s["rates"])
+            spec = dict(helpers.DEFAULT, seed=9, length=(2500.0, 2200.0), rates=(5.0, 5.0, 10.0), glitch=(900.0, 25.0, 25.0))
+            w = orc.workload(spec["seed"])
+            w.set_length(*spec["length"]); w.set_references(fasta, adjusted=True); w.set_identity(*spec["identity"])
+            w.set_adapter(*spec["adapter"]); w.set_glitch(*spec["glitch"]); w.set_error_model(None); w.set_qscore_model("random")
             self.w = w
-            self.fed = 0
         def __call__(self, descs):
-            raise NotImplementedError
-    # the oracle generates whole batches; pick this rank's range out of it
-    class Gen:
-        def __init__(self, sim):
-            self.o = OracleGenerator(sim); self.sim = sim
-        def run(self, base_loop, lo, hi, emitted_prev):
-            w = self.o.w
-            for _ in range(2 * emitted_prev):
-                orc.lib.orc_rng_next_u64(w.rng_handle())   # the reference writer's u128 draws of the previous batch
-            n = w.feed(base_loop); w.generate(threads=2, keep_cigar_raw=False)
-            seq, so = w.out("seq"); qual, _ = w.out("qual"); ident = w.out_identity()
-            lens = (so[1:] - so[:-1]).astype(np.uint64)
-            a, b = int(so[lo]), int(so[hi])
-            return ((so[lo:hi + 1] - so[lo]).astype(np.uint64), lens[lo:hi], seq[a:b].copy(), qual[a:b].copy(), ident[lo:hi].copy())
+            w = self.w
+            w.load_items(*capi.descs_to_item_table(descs))
+            if len(descs) == 0:
+                return (np.zeros(1, np.uint64), np.zeros(0, np.uint64), np.zeros(0, np.uint8), np.zeros(0, np.uint8), np.zeros(0, np.float64))
+            w.generate(threads=2, keep_cigar_raw=False)
+            seq, so = w.out("seq"); qual, _ = w.out("qual")
+            return (so, (so[1:] - so[:-1]).astype(np.uint64), seq[:int(so[-1])], qual[:int(so[-1])], w.out_identity())
 
-    # drive simulate() with a generate_fn that needs the batch context: wrap feed to capture it
-    state = dict(base_loop=None, emitted_prev=0, bounds=None)
-    gen_holder = {}
-    def factory(sim):
-        g = Gen(sim); gen_holder["g"] = g
-        orig_feed = sim.feed
-        def feed(base_loop):
-            state["base_loop"] = base_loop
-            d = orig_feed(base_loop)
-            state["bounds"] = S.shard_bounds(d, world)
-            return d
-        sim.feed = feed
-        orig_skip = sim.skip_names
-        def call(descs):
-            lo, hi = state["bounds"][rank], state["bounds"][rank + 1]
-            out = g.run(state["base_loop"], lo, hi, state["emitted_prev"])
-            return out
-        return call
-    # emitted count of the previous batch is needed by every rank's oracle: recompute it from lengths (len > 14)
-    import io
     out = io.BytesIO() if rank == 0 else None
-    class CountingSim: pass
-    orig_simulate_fastq = capi.Simulation.fastq
-    def fastq(self, b, first=0):
-        t, r, bs = orig_simulate_fastq(self, b, first)
-        state["emitted_batch"] = state.get("emitted_batch", 0) + r
-        return t, r, bs
-    capi.Simulation.fastq = fastq
-    orig_skip = capi.Simulation.skip_names
-    def skip(self, n):
-        state["emitted_prev"] = n
-        return orig_skip(self, n)
-    capi.Simulation.skip_names = skip
-    orig_feed_cls = capi.Simulation.feed
-    def feed_cls(self, base_loop):
-        if rank == 0:
-            state["emitted_prev"] = state.pop("emitted_batch", 0)
-        return orig_feed_cls(self, base_loop)
-    capi.Simulation.feed = feed_cls
-    reads, bases = S.simulate(fasta, "10x", out, generate_factory=factory, dist=dist, rank=rank, world=world, seed=9, length="2500,2200",
+    reads, bases = S.simulate(fasta, "10x", out, generate_factory=OracleGenerator, dist=dist, rank=rank, world=world, seed=9, length="2500,2200",
                               junk_reads=5.0, random_reads=5.0, chimera=10.0, glitches="900,25,25", error_model="random", qscore_model="random",
                               number_base_store="300K")
     if rank == 0:
