@@ -88,9 +88,9 @@ class ClockSampler:
 
     def _pump(self):
         for line in self.proc.stdout:
-            self.lines.append(line.strip())
+            self.lines.append((time.time(), line.strip()))
 
-    def stop(self):
+    def stop(self, t0=None, t1=None):
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
@@ -100,7 +100,12 @@ class ClockSampler:
             self.proc.kill()
         sm, mx, reasons, power = [], [], set(), []
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for l in self.lines:
+        inside = [l for (t, l) in self.lines if t0 is None or (t0 <= t <= t1 + 0.2)]
+        window = "timed region"
+        if not inside:  # a short timed region can fall between two samples: use the warm-up of the same kernels
+            inside = [l for (_, l) in self.lines]
+            window = "warm-up + timed region (no sample fell inside the timed region)"
+        for l in inside:
             f = [x.strip() for x in l.split(",")]
             if len(f) < 7:
                 continue
@@ -116,7 +121,7 @@ class ClockSampler:
         if not sm:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
         return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons), "samples": len(sm),
-                "power_w_max": max(power) if power else None}
+                "power_w_max": max(power) if power else None, "window": window}
 
 
 def cpu_baseline(fasta, coverage, threads):
@@ -179,6 +184,8 @@ def main():
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; rustyread_b200 has no CPU fallback")
+    from rustyread_b200.placement import bind_to_gpu_numa
+    placement = bind_to_gpu_numa(local_rank)  # before any pinned allocation: keep the D2H drain on the GPU's socket
     torch.cuda.set_device(local_rank)
     dist = None
     if world > 1:
@@ -212,11 +219,12 @@ def main():
 
     # ---- resident-in-HBM timing: kernels only --------------------------------------------------------------
     ctx.upload(descs)
+    sampler = ClockSampler(local_rank)
+    sampler.start()
     for _ in range(max(args.warmup, 3)):
         ctx.run()
     barrier()
-    sampler = ClockSampler(local_rank)
-    sampler.start()
+    t_timed0 = time.time()
     l0 = ctx.kernel_launches()
     dev_ms, read_ms, q_ms, pack_ms = 0.0, 0.0, 0.0, 0.0
     bases = 0
@@ -235,8 +243,9 @@ def main():
         pack_ms += ms["pack"]
         bases += ctx.last_run_bases()
     launches = ctx.kernel_launches() - l0
+    t_timed1 = time.time()
     barrier()
-    clocks = sampler.stop()
+    clocks = sampler.stop(t_timed0, t_timed1)
 
     # ---- end to end through the public call: host buffers in, host buffers out, every step ----------------------
     b = ctx.generate(descs)  # warm the pinned staging buffers
@@ -279,7 +288,7 @@ def main():
             "metric": "simulated bases/sec", "value": value, "unit": "bases/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": dev_ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
             "config": {"workload": WORKLOAD, "reads_per_step_per_gpu": n_reads, "bases_per_step_per_gpu": int(per_launch_bases),
-                       "sharding": "rank r takes batch r of the seeded feeder; no data-path collective",
+                       "sharding": "rank r takes batch r of the seeded feeder; no data-path collective", "host_placement_rank0": placement,
                        "l2": "explicit 256 MiB L2 flush between timed steps; per-step working set (raw+err+cigar+qual arenas, ~4.6 GB) also exceeds the 126 MB L2"},
             "e2e": {"value": tot_e2e_bases / e2e_s_max, "unit": "bases/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
             "gpu_launches": int(tot_launches),

@@ -28,6 +28,8 @@ def main(argv=None):
     a = ap.parse_args(argv)
 
     rank, world, local = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("LOCAL_RANK", "0"))
+    from .placement import bind_to_gpu_numa
+    bind_to_gpu_numa(local)  # keep the pinned drain buffers on the GPU's socket
     dist = None
     if world > 1:
         import torch.distributed as dist
