@@ -237,8 +237,14 @@ __device__ __forceinline__ void st_emit_seq(Stitch& S, const uint8_t* q, uint32_
 // AbsChanges::add_change (src/simulate/error.rs:173-193) with contain / overlap / merge /
 // update_align (error.rs:83-164).  Returns the edit count to subtract from the target.
 // One alignment call site: the merge and the push cases only differ in which slices are aligned.
+// `fk` != 0 says that oseq is raw[ob..oe) with ONE random edit of kind fk (1 substitution, 2 insertion, 3 deletion) at
+// offset fep (random_error, src/model/error.rs:116-135).  When such a change is pushed (not merged), the CIGAR of the
+// reference's LCS alignment has a closed form, so no DP is run: the suffix after the edit matches on the diagonal,
+// the edit then slides left through equal neighbours (a match always takes the diagonal), and where it stops the
+// prefixes are identical, which forces X / I / D there.  Checked exhaustively against the DP + tie-break for all
+// k-mers up to k = 7 over 1-, 2- and 4-letter alphabets.
 __device__ __forceinline__ uint32_t add_change(Stitch& S, WarpSmem* ws, const ReadKernelParams& P, uint32_t gwarp, uint32_t ob, uint32_t oe,
-                                               const uint8_t* oseq, uint32_t olen, int lane) {
+                                               const uint8_t* oseq, uint32_t olen, uint32_t fk, uint32_t fep, int lane) {
   bool merge = false;
   uint32_t es = 0, rs, re;
   if (S.has_last) {
@@ -285,6 +291,21 @@ __device__ __forceinline__ uint32_t add_change(Stitch& S, WarpSmem* ws, const Re
     if (gap) st_emit_gap(S, gap, lane);
     st_emit_seq(S, oseq + es, add, lane);
     dst = S.cig + S.cig_len;
+  }
+  if (!merge && fk) {
+    const uint8_t* t = S.raw + ob;
+    uint32_t at = fep;  // where the non-'=' op lands
+    if (fk != 1) {
+      // slide left while the base left of the edit equals the one it would be swapped with
+      const bool c = (uint32_t)lane >= 1 && (uint32_t)lane <= fep && (fk == 2 ? oseq[lane] == t[lane - 1] : t[lane - 1] == t[lane]);
+      const uint32_t B = __ballot_sync(0xffffffffu, c);
+      at = fep - __clz(~(B << (31 - fep)));
+    }
+    const uint32_t total = fk == 2 ? olen : tn;  // substitution k, insertion k + 1, deletion k ops
+    if (dst && (uint32_t)lane < total) dst[lane] = (uint32_t)lane == at ? (fk == 1 ? 'X' : fk == 2 ? 'I' : 'D') : '=';
+    if (S.l_emit) S.cig_len += total;
+    S.ledit += 1;
+    return 1;
   }
   const uint64_t a = warp_align(ws, P, gwarp, oseq + es, add, S.raw + rs, tn, dst, lane);
   if (align_status(a)) { S.status = align_status(a); return 0; }
@@ -365,7 +386,7 @@ __device__ __forceinline__ void process_read(const ReadKernelParams& P, WarpSmem
         glitch_checked = false;
       }
       if (!(ff & 1u)) break;  // pos == L - k
-      uint32_t ob, oe, olen;
+      uint32_t ob, oe, olen, fk = 0, fep = 0;
       const uint8_t* oseq;
       const bool is_glitch = (ff & 2u) != 0;
       if (is_glitch) {  // glitch due at pos (error.rs:282-287)
@@ -415,12 +436,14 @@ __device__ __forceinline__ void process_read(const ReadKernelParams& P, WarpSmem
           }
           __syncwarp();
           olen = n;
+          fk = kind;
+          fep = ep;
         }
         ob = pos;
         oe = pos + k;
         oseq = ws->alt;
       }
-      target -= (double)add_change(S, ws, P, gwarp, ob, oe, oseq, olen, lane);
+      target -= (double)add_change(S, ws, P, gwarp, ob, oe, oseq, olen, fk, fep, lane);
       if (S.status) break;
       if (is_glitch) {
         glitch_checked = true;  // same pos again, with the new target, glitch check done
