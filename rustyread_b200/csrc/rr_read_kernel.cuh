@@ -238,14 +238,15 @@ __device__ __forceinline__ void st_emit_seq(Stitch& S, const uint8_t* q, uint32_
 // update_align (error.rs:83-164).  Returns the edit count to subtract from the target.
 // One alignment call site: the merge and the push cases only differ in which slices are aligned.
 // `fk` != 0 says that oseq is raw[ob..oe) with ONE random edit of kind fk (1 substitution, 2 insertion, 3 deletion) at
-// offset fep (random_error, src/model/error.rs:116-135).  When such a change is pushed (not merged), the CIGAR of the
-// reference's LCS alignment has a closed form, so no DP is run: the suffix after the edit matches on the diagonal,
-// the edit then slides left through equal neighbours (a match always takes the diagonal), and where it stops the
-// prefixes are identical, which forces X / I / D there.  Checked exhaustively against the DP + tie-break for all
-// k-mers up to k = 7 over 1-, 2- and 4-letter alphabets.
+// offset fep (random_error, src/model/error.rs:116-135).  When such a change is pushed, or merged into a last change
+// whose raw and err ends coincide, the piece that gets aligned is a k-mer tail against the same tail with at most one
+// edit, and the CIGAR of the reference's LCS alignment has a closed form, so no DP is run: the suffix after the edit
+// matches on the diagonal, the edit then slides left through equal neighbours (a match always takes the diagonal),
+// and where it stops the prefixes are identical, which forces X / I / D there.  Checked against the DP + tie-break
+// exhaustively for all k-mers up to k = 7 over 1-, 2- and 4-letter alphabets and for every piece offset.
 __device__ __forceinline__ uint32_t add_change(Stitch& S, WarpSmem* ws, const ReadKernelParams& P, uint32_t gwarp, uint32_t ob, uint32_t oe,
                                                const uint8_t* oseq, uint32_t olen, uint32_t fk, uint32_t fep, int lane) {
-  bool merge = false;
+  bool merge = false, piece_fast = fk != 0;  // closed form applies to a pushed change, and to some merges (below)
   uint32_t es = 0, rs, re;
   if (S.has_last) {
     const uint32_t l_end_err = S.lb + S.lseq_len;
@@ -256,12 +257,16 @@ __device__ __forceinline__ uint32_t add_change(Stitch& S, WarpSmem* ws, const Re
       if (ob < l_end_err) {
         es = l_end_err - ob;  // olen > es holds because the change is not contained
         S.le = S.le + oe - ob - es;
+        // If the last change consumed as many raw bases as it produced (old_end == l_end_err), the appended piece
+        // oseq[es..] faces exactly raw[ob + es .. oe): the same k-mer tail, so the single-edit closed form still holds.
+        piece_fast = piece_fast && old_end == l_end_err;
       } else {
         S.le = ob + olen;
+        piece_fast = false;
       }
       if (S.le < S.L - 1) {
         if (old_end < S.le) { rs = old_end; re = S.le; } else { rs = S.le; re = old_end; }
-      } else { rs = old_end; re = S.L; }
+      } else { rs = old_end; re = S.L; piece_fast = false; }
       if (rs > re || re > S.L || es > olen) { S.status = ST_REF_PANIC; return 0; }
       S.lseq_len += olen - es;
     }
@@ -292,20 +297,24 @@ __device__ __forceinline__ uint32_t add_change(Stitch& S, WarpSmem* ws, const Re
     st_emit_seq(S, oseq + es, add, lane);
     dst = S.cig + S.cig_len;
   }
-  if (!merge && fk) {
-    const uint8_t* t = S.raw + ob;
-    uint32_t at = fep;  // where the non-'=' op lands
+  if (piece_fast) {
+    const uint8_t* q = oseq + es;
+    const uint8_t* t = S.raw + rs;
+    const uint32_t e = fep >= es ? fep - es : 0;    // where the edit sits inside the piece (an edit left of it acts at 0)
+    const bool has_edit = !(fk == 1 && fep < es);   // a substitution in the overlapped part leaves the piece identical
+    uint32_t at = e;                                // where the non-'=' op lands
     if (fk != 1) {
       // slide left while the base left of the edit equals the one it would be swapped with
-      const bool c = (uint32_t)lane >= 1 && (uint32_t)lane <= fep && (fk == 2 ? oseq[lane] == t[lane - 1] : t[lane - 1] == t[lane]);
+      const bool c = (uint32_t)lane >= 1 && (uint32_t)lane <= e && (fk == 2 ? q[lane] == t[lane - 1] : t[lane - 1] == t[lane]);
       const uint32_t B = __ballot_sync(0xffffffffu, c);
-      at = fep - __clz(~(B << (31 - fep)));
+      at = e - __clz(~(B << (31 - e)));
     }
-    const uint32_t total = fk == 2 ? olen : tn;  // substitution k, insertion k + 1, deletion k ops
-    if (dst && (uint32_t)lane < total) dst[lane] = (uint32_t)lane == at ? (fk == 1 ? 'X' : fk == 2 ? 'I' : 'D') : '=';
+    const uint32_t total = fk == 2 ? add : tn;  // substitution / deletion: one op per raw base, insertion: one per piece base
+    if (dst && (uint32_t)lane < total) dst[lane] = (has_edit && (uint32_t)lane == at) ? (fk == 1 ? 'X' : fk == 2 ? 'I' : 'D') : '=';
     if (S.l_emit) S.cig_len += total;
-    S.ledit += 1;
-    return 1;
+    const uint32_t ed = has_edit ? 1u : 0u;
+    S.ledit += ed;
+    return ed;
   }
   const uint64_t a = warp_align(ws, P, gwarp, oseq + es, add, S.raw + rs, tn, dst, lane);
   if (align_status(a)) { S.status = align_status(a); return 0; }
