@@ -67,6 +67,7 @@ struct rr_ctx {
   double glitch_mean_dist = 0, glitch_mean_size = 0;
   DevBuf d_ref, d_ref_off, d_ref_circ;
   DevBuf d_em_index, d_em_alt_begin, d_em_alt_off, d_em_alt_bytes, d_em_cum, d_em_scale;
+  DevBuf d_em_piece_begin, d_em_piece_off, d_em_piece_edits, d_em_piece_ops;
   DevBuf d_adapter;
   DevBuf d_q_tab_off, d_q_tab, d_q_dist_off, d_q_scores, d_q_cum, d_q_scale, d_q_unit;
 
@@ -165,7 +166,8 @@ RR_API void rr_destroy(rr_ctx* ctx) {
   cudaStreamSynchronize(ctx->stream);
   cudaStreamSynchronize(ctx->copy_stream);
   DevBuf* bufs[] = {&ctx->d_ref, &ctx->d_ref_off, &ctx->d_ref_circ, &ctx->d_em_index, &ctx->d_em_alt_begin, &ctx->d_em_alt_off,
-                    &ctx->d_em_alt_bytes, &ctx->d_em_cum, &ctx->d_em_scale, &ctx->d_adapter, &ctx->d_q_tab_off, &ctx->d_q_tab,
+                    &ctx->d_em_alt_bytes, &ctx->d_em_cum, &ctx->d_em_scale, &ctx->d_em_piece_begin, &ctx->d_em_piece_off, &ctx->d_em_piece_edits,
+                    &ctx->d_em_piece_ops, &ctx->d_adapter, &ctx->d_q_tab_off, &ctx->d_q_tab,
                     &ctx->d_q_dist_off, &ctx->d_q_scores, &ctx->d_q_cum, &ctx->d_q_scale, &ctx->d_q_unit, &ctx->d_raw, &ctx->d_err, &ctx->d_cig,
                     &ctx->d_sc_rows, &ctx->d_sc_ops, &ctx->d_sc_grec, &ctx->d_sc_gseq};
   for (auto* b : bufs) b->release();
@@ -217,6 +219,35 @@ RR_API int rr_set_references(rr_ctx* ctx, uint64_t n, const uint8_t* const* seq,
   return RR_OK;
 }
 
+// alignment::align on the host (src/alignment.rs:13-41: bio's global aligner with match 1, everything else 0 = LCS with
+// the traceback preference diag >= left && diag >= up -> diag, else up >= left -> I, else D).  Used once per model
+// alternative at load time; the kernels use bit-vector forms of the same rule.
+static uint32_t host_align(const uint8_t* q, uint32_t m, const uint8_t* t, uint32_t n, std::vector<uint8_t>& ops) {
+  std::vector<uint16_t> S((size_t)(m + 1) * (n + 1), 0);
+  const size_t W = n + 1;
+  for (uint32_t i = 1; i <= m; ++i)
+    for (uint32_t j = 1; j <= n; ++j)
+      S[i * W + j] = std::max<uint16_t>((uint16_t)(S[(i - 1) * W + j - 1] + (q[i - 1] == t[j - 1] ? 1 : 0)), std::max(S[(i - 1) * W + j], S[i * W + j - 1]));
+  std::vector<uint8_t> rev;
+  uint32_t i = m, j = n, edits = 0;
+  while (i > 0 || j > 0) {
+    uint8_t op;
+    if (i == 0) { op = 'D'; --j; }
+    else if (j == 0) { op = 'I'; --i; }
+    else {
+      const bool eq = q[i - 1] == t[j - 1];
+      const int dg = S[(i - 1) * W + j - 1] + (eq ? 1 : 0), up = S[(i - 1) * W + j], left = S[i * W + j - 1];
+      if (dg >= left && dg >= up) { op = eq ? '=' : 'X'; --i; --j; }
+      else if (up >= left) { op = 'I'; --i; }
+      else { op = 'D'; --j; }
+    }
+    edits += op != '=';
+    rev.push_back(op);
+  }
+  ops.insert(ops.end(), rev.rbegin(), rev.rend());
+  return edits;
+}
+
 // ---- error model ---------------------------------------------------------------------------------------
 RR_API int rr_set_error_model(rr_ctx* ctx, uint32_t k, uint64_t n_keys, const uint8_t* keys, const uint32_t* alt_begin,
                               const uint32_t* alt_off, const uint8_t* alt_bytes, const double* weights) {
@@ -253,8 +284,27 @@ RR_API int rr_set_error_model(rr_ctx* ctx, uint32_t k, uint64_t n_keys, const ui
   }
   std::vector<uint32_t> ab(alt_begin, alt_begin + n_keys + 1), ao(alt_off, alt_off + n_alts + 1);
   std::vector<uint8_t> bytes(alt_bytes, alt_bytes + alt_off[n_alts]);
+  // precomputed alignments: alternative j (of key i) against its key, for every piece offset es < len(alt), es <= k
+  std::vector<uint32_t> piece_begin(n_alts + 1, 0), piece_off(1, 0);
+  std::vector<uint8_t> piece_edits, piece_ops;
+  for (uint64_t i = 0; i < n_keys; ++i) {
+    const uint8_t* key = keys + i * k;
+    for (uint32_t j = alt_begin[i]; j < alt_begin[i + 1]; ++j) {
+      const uint8_t* alt = alt_bytes + alt_off[j];
+      const uint32_t al = alt_off[j + 1] - alt_off[j];
+      piece_begin[j] = (uint32_t)piece_edits.size();
+      for (uint32_t es = 0; es < std::max(1u, al) && es <= k; ++es) {
+        const uint32_t e = host_align(alt + std::min(es, al), al - std::min(es, al), key + es, k - es, piece_ops);
+        piece_edits.push_back((uint8_t)std::min(e, 255u));
+        piece_off.push_back((uint32_t)piece_ops.size());
+      }
+    }
+  }
+  piece_begin[n_alts] = (uint32_t)piece_edits.size();
   if (!upload(ctx, ctx->d_em_index, index) || !upload(ctx, ctx->d_em_alt_begin, ab) || !upload(ctx, ctx->d_em_alt_off, ao) ||
-      !upload(ctx, ctx->d_em_alt_bytes, bytes) || !upload(ctx, ctx->d_em_cum, cum) || !upload(ctx, ctx->d_em_scale, scale))
+      !upload(ctx, ctx->d_em_alt_bytes, bytes) || !upload(ctx, ctx->d_em_cum, cum) || !upload(ctx, ctx->d_em_scale, scale) ||
+      !upload(ctx, ctx->d_em_piece_begin, piece_begin) || !upload(ctx, ctx->d_em_piece_off, piece_off) ||
+      !upload(ctx, ctx->d_em_piece_edits, piece_edits) || !upload(ctx, ctx->d_em_piece_ops, piece_ops))
     return fail(ctx, RR_ERR_CUDA, "rr_set_error_model: upload failed");
   ctx->M.em_index = ctx->d_em_index.as<int32_t>();
   ctx->M.em_alt_begin = ctx->d_em_alt_begin.as<uint32_t>();
@@ -262,6 +312,10 @@ RR_API int rr_set_error_model(rr_ctx* ctx, uint32_t k, uint64_t n_keys, const ui
   ctx->M.em_alt_bytes = ctx->d_em_alt_bytes.as<uint8_t>();
   ctx->M.em_cum = ctx->d_em_cum.as<double>();
   ctx->M.em_scale = ctx->d_em_scale.as<double>();
+  ctx->M.em_piece_begin = ctx->d_em_piece_begin.as<uint32_t>();
+  ctx->M.em_piece_off = ctx->d_em_piece_off.as<uint32_t>();
+  ctx->M.em_piece_edits = ctx->d_em_piece_edits.as<uint8_t>();
+  ctx->M.em_piece_ops = ctx->d_em_piece_ops.as<uint8_t>();
   ctx->have_error = true;
   return RR_OK;
 }

@@ -188,7 +188,7 @@ __device__ __noinline__ StageOut stage_alt_from_table(WarpRng rng, const DeviceM
   o.base = rng.base;
   o.cur = rng.cursor();
   o.value = n;
-  o.status = ST_OK;
+  o.status = a0 + idx;  // global id of the chosen alternative (indexes the precomputed alignments)
   return o;
 }
 
@@ -244,6 +244,8 @@ __device__ __forceinline__ void st_emit_seq(Stitch& S, const uint8_t* q, uint32_
 // matches on the diagonal, the edit then slides left through equal neighbours (a match always takes the diagonal),
 // and where it stops the prefixes are identical, which forces X / I / D there.  Checked against the DP + tie-break
 // exhaustively for all k-mers up to k = 7 over 1-, 2- and 4-letter alphabets and for every piece offset.
+// fk == 4: oseq is alternative `fep` of the error-model table for the k-mer raw[ob..oe); its alignments against the key
+// (whole, and every tail piece) were computed at load time with the same rule, so they are copied instead of recomputed.
 __device__ __forceinline__ uint32_t add_change(Stitch& S, WarpSmem* ws, const ReadKernelParams& P, uint32_t gwarp, uint32_t ob, uint32_t oe,
                                                const uint8_t* oseq, uint32_t olen, uint32_t fk, uint32_t fep, int lane) {
   bool merge = false, piece_fast = fk != 0;  // closed form applies to a pushed change, and to some merges (below)
@@ -259,7 +261,7 @@ __device__ __forceinline__ uint32_t add_change(Stitch& S, WarpSmem* ws, const Re
         S.le = S.le + oe - ob - es;
         // If the last change consumed as many raw bases as it produced (old_end == l_end_err), the appended piece
         // oseq[es..] faces exactly raw[ob + es .. oe): the same k-mer tail, so the single-edit closed form still holds.
-        piece_fast = piece_fast && old_end == l_end_err;
+        piece_fast = piece_fast && old_end == l_end_err && es <= oe - ob;  // (a longer overlap makes the raw slice run backwards)
       } else {
         S.le = ob + olen;
         piece_fast = false;
@@ -296,6 +298,16 @@ __device__ __forceinline__ uint32_t add_change(Stitch& S, WarpSmem* ws, const Re
     if (gap) st_emit_gap(S, gap, lane);
     st_emit_seq(S, oseq + es, add, lane);
     dst = S.cig + S.cig_len;
+  }
+  if (piece_fast && fk == 4) {
+    const DeviceModels& M = P.M;
+    const uint32_t pi = M.em_piece_begin[fep] + es;
+    const uint32_t o0 = M.em_piece_off[pi], total = M.em_piece_off[pi + 1] - o0;
+    const uint32_t ed = M.em_piece_edits[pi];
+    if (dst) for (uint32_t x = lane; x < total; x += 32) dst[x] = M.em_piece_ops[o0 + x];
+    if (S.l_emit) S.cig_len += total;
+    S.ledit += ed;
+    return ed;
   }
   if (piece_fast) {
     const uint8_t* q = oseq + es;
@@ -428,6 +440,8 @@ __device__ __forceinline__ void process_read(const ReadKernelParams& P, WarpSmem
           so = stage_alt_from_table(rng, M, ws, key);
           rng.set_cursor(so.base, so.cur);
           olen = (uint32_t)so.value;
+          fk = 4;
+          fep = so.status;
         } else {  // random_error (src/model/error.rs:116-135)
           const uint32_t ep = (uint32_t)rng.gen_range_u64(0, k - 1);
           const uint32_t kind = rng.gen_range_u32(1, 3);  // 1 substitution, 2 insertion, 3 deletion
