@@ -3,7 +3,9 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
+#include <ctime>
 #include <map>
 #include <numeric>
 #include <string>
@@ -102,6 +104,15 @@ struct rr_ctx {
   DevBuf d_sc_rows, d_sc_ops, d_sc_grec, d_sc_gseq;
   uint64_t sc_rows_cap = 32768, sc_ops_cap = 8192, sc_grec_cap = 0, sc_gseq_cap = 0;
 };
+
+// RR_TRACE=1: host-side timeline of the batch pipeline on stderr (developer aid, off by default)
+static const bool g_trace = std::getenv("RR_TRACE") != nullptr;
+static void trace(const char* what, uint64_t batch) {
+  if (!g_trace) return;
+  timespec ts;
+  clock_gettime(CLOCK_MONOTONIC, &ts);
+  std::fprintf(stderr, "[rr %.3f ms] batch %llu %s\n", ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6, (unsigned long long)batch, what);
+}
 
 static int fail(rr_ctx* c, int code, const std::string& msg) {
   if (c) c->err = msg; else g_create_error = msg;
@@ -466,7 +477,10 @@ static int plan(rr_ctx* ctx, Slot& sl) {
   sl.h_raw_off.assign(n + 1, 0);
   sl.h_out_off.assign(n + 1, 0);
   sl.h_order.resize(n);
-  std::vector<uint64_t> raw_cap(n);
+  // Processing order = longest estimated WORK first.  The walk costs about 400 warp instructions per error event and
+  // about 5 per base (profiles/), and the events of a read are a serial chain, so the read with the most events (not
+  // the most bases) is the critical path of a batch and has to start first.
+  std::vector<double> work(n);
   double max_ng = 0;
   for (uint64_t i = 0; i < n; ++i) {
     const rr_desc& d = sl.descs[i];
@@ -477,8 +491,8 @@ static int plan(rr_ctx* ctx, Slot& sl) {
     if (!(d.identity <= 1.0 && d.identity >= -1.0)) return fail(ctx, RR_ERR_ARG, "rr_upload: identity outside [0,1]");
     uint64_t rcap = 2ULL * M.k + f1 + f2 + 2 * adapters;
     if (rcap >= (1ULL << 30)) return fail(ctx, RR_ERR_UNSUPPORTED, "rr_upload: a single read of 2^30 bases or more");
-    raw_cap[i] = rcap;
     double target = std::max(0.0, (1.0 - d.identity)) * (double)rcap;
+    work[i] = 80.0 * target + (double)rcap;
     double ng = 0, gl = 0;
     if (M.has_distance) {
       ng = (double)rcap / (ctx->glitch_mean_dist + 1.0);
@@ -491,7 +505,7 @@ static int plan(rr_ctx* ctx, Slot& sl) {
     sl.h_out_off[i + 1] = sl.h_out_off[i] + ocap;
   }
   std::iota(sl.h_order.begin(), sl.h_order.end(), 0u);
-  std::stable_sort(sl.h_order.begin(), sl.h_order.end(), [&](uint32_t a, uint32_t b) { return raw_cap[a] > raw_cap[b]; });
+  std::stable_sort(sl.h_order.begin(), sl.h_order.end(), [&](uint32_t a, uint32_t b) { return work[a] > work[b]; });
   sl.sc_grec_cap = (uint64_t)max_ng + 8;
   sl.sc_gseq_cap = align16((uint64_t)(max_ng * (ctx->glitch_mean_size + 1.0)) + 64);
   return RR_OK;
@@ -744,10 +758,13 @@ RR_API int rr_submit(rr_ctx* ctx, uint64_t n, const rr_desc* descs) {
   if (!ctx) return RR_ERR_ARG;
   if (ctx->n_submitted - ctx->n_collected >= 2) return fail(ctx, RR_ERR_ARG, "rr_submit: two batches already in flight (rr_collect one first)");
   Slot& sl = ctx->slot[ctx->n_submitted & 1];
+  trace("submit: begin", ctx->n_submitted);
   int rc = prepare(ctx, sl, n, descs);
   if (rc) return rc;
+  trace("submit: plan + H2D queued", ctx->n_submitted);
   rc = enqueue(ctx, sl);
   if (rc) return rc;
+  trace("submit: kernels queued", ctx->n_submitted);
   ctx->n_submitted += 1;
   return RR_OK;
 }
@@ -758,9 +775,13 @@ RR_API int rr_collect(rr_ctx* ctx, rr_batch* out) {
   CK(cudaSetDevice(ctx->device));
   Slot& sl = ctx->slot[ctx->n_collected & 1];
   ctx->n_collected += 1;
+  trace("collect: begin", ctx->n_collected - 1);
   int rc = finish(ctx, sl);
   if (rc) return rc;
-  return fetch(ctx, sl, out);
+  trace("collect: kernels done", ctx->n_collected - 1);
+  rc = fetch(ctx, sl, out);
+  trace("collect: D2H done", ctx->n_collected - 1);
+  return rc;
 }
 
 RR_API int rr_generate(rr_ctx* ctx, uint64_t n, const rr_desc* descs, rr_batch* out) {
