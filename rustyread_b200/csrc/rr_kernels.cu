@@ -102,7 +102,7 @@ struct rr_ctx {
   uint64_t n_replans = 0;      // how many times a batch had to be re-planned with more slack
   DevBuf d_raw, d_err, d_cig;
   DevBuf d_sc_rows, d_sc_ops, d_sc_grec, d_sc_gseq;
-  uint64_t sc_rows_cap = 32768, sc_ops_cap = 8192, sc_grec_cap = 0, sc_gseq_cap = 0;
+  uint64_t sc_rows_cap = 32768, sc_ops_cap = 16384, sc_grec_cap = 0, sc_gseq_cap = 0;
 };
 
 // RR_TRACE=1: host-side timeline of the batch pipeline on stderr (developer aid, off by default)
@@ -453,6 +453,7 @@ RR_API int rr_set_glitch(rr_ctx* ctx, double rate, double size, double skip) {
 
 // ---- batch planning ------------------------------------------------------------------------------------------
 static inline uint64_t align16(uint64_t x) { return (x + 15) & ~15ULL; }
+static inline uint64_t align128(uint64_t x) { return (x + 127) & ~127ULL; }
 typedef rr_ctx::Slot Slot;
 
 static int frag_len(rr_ctx* ctx, uint32_t type, uint32_t ref_idx, uint64_t start, uint64_t end, uint64_t& out) {
@@ -500,7 +501,8 @@ static int plan(rr_ctx* ctx, Slot& sl) {
       gl = ng * (ctx->glitch_mean_size + 1.0);
       max_ng = std::max(max_ng, ng);
     }
-    uint64_t ocap = align16(rcap + (uint64_t)std::ceil(target) + (uint64_t)gl + (uint64_t)(64 * sl.slack) + ALT_MAX + 16);
+    // err / CIGAR leave the kernel in 128-byte chunks and the capacity test keeps two chunks of margin (flush_chunks)
+    uint64_t ocap = align128(rcap + (uint64_t)std::ceil(target) + (uint64_t)gl + (uint64_t)(64 * sl.slack) + ALT_MAX + 16 + 3 * CHUNK);
     sl.h_raw_off[i + 1] = sl.h_raw_off[i] + align16(rcap + 16);
     sl.h_out_off[i + 1] = sl.h_out_off[i] + ocap;
   }

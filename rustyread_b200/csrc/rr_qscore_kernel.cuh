@@ -190,7 +190,17 @@ __global__ void __launch_bounds__(256) rr_pack_kernel(const __grid_constant__ Pa
     const uint4* src = reinterpret_cast<const uint4*>(P.err + P.out_off[r]);
     uint4* dst = reinterpret_cast<uint4*>(P.seq + P.packed_off[r]);
     const uint64_t nv = (n + 15) / 16;  // capacity is padded to 16 on both sides
-    for (uint64_t i = threadIdx.x; i < nv; i += blockDim.x) dst[i] = src[i];
+    for (uint64_t i = threadIdx.x; i < nv; i += blockDim.x) {
+      uint4 v = src[i];
+      if (16 * i + 16 > n) {  // last word: the padding after the read is zeroed (what lies beyond err_len in the arena is stale staging data)
+        uint32_t w[4] = {v.x, v.y, v.z, v.w};
+        const uint32_t keep = (uint32_t)(n - 16 * i);
+#pragma unroll
+        for (uint32_t j = 0; j < 4; ++j) w[j] = keep >= 4 * j + 4 ? w[j] : (keep > 4 * j ? (w[j] & ((1u << (8 * (keep - 4 * j))) - 1u)) : 0u);
+        v = make_uint4(w[0], w[1], w[2], w[3]);
+      }
+      dst[i] = v;
+    }
   }
 }
 

@@ -167,8 +167,9 @@ __device__ __noinline__ StageOut stage_glitches(WarpRng rng, const ReadKernelPar
 }
 
 // Error::add_errors_to_kmer on a k-mer that is in the table (src/model/error.rs:96-100): one WeightedIndex draw.
-// Out of line: only file models reach it.  value = alternative length (bytes in ws->alt).
-__device__ __noinline__ StageOut stage_alt_from_table(WarpRng rng, const DeviceModels& M, WarpSmem* ws, int key) {
+// Out of line: only file models reach it.  value = alternative length, status = global id of the chosen alternative
+// (it indexes em_alt_off and the precomputed alignments).
+__device__ __noinline__ StageOut stage_alt_from_table(WarpRng rng, const DeviceModels& M, int key) {
   const int lane = rng.lane;
   uint32_t a0 = M.em_alt_begin[key], a1 = M.em_alt_begin[key + 1];
   uint32_t na = a1 - a0;
@@ -179,160 +180,302 @@ __device__ __noinline__ StageOut stage_alt_from_table(WarpRng rng, const DeviceM
     bool le = (i + 1 < na) && (M.em_cum[a0 + i] <= chosen);
     idx += __popc(__ballot_sync(0xffffffffu, le));
   }
-  uint32_t o0 = M.em_alt_off[a0 + idx], o1 = M.em_alt_off[a0 + idx + 1];
-  uint32_t n = o1 - o0;
-  __syncwarp();
-  for (uint32_t i = lane; i < n; i += 32) ws->alt[i] = M.em_alt_bytes[o0 + i];
-  __syncwarp();
   StageOut o;
   o.base = rng.base;
   o.cur = rng.cursor();
-  o.value = n;
-  o.status = a0 + idx;  // global id of the chosen alternative (indexes the precomputed alignments)
+  o.value = M.em_alt_off[a0 + idx + 1] - M.em_alt_off[a0 + idx];
+  o.status = a0 + idx;
   return o;
 }
 
 // State of `changes.last()` plus the streamed stitch of sequence() (src/simulate/error.rs:219-246).
 // A Change only ever grows by appending to seq / cigar (merge, error.rs:105-152), and only the last
-// one can change, so err / CIGAR are written once, in order, as the walk proceeds.
-// All positions are 32-bit: the host refuses reads whose raw capacity reaches 2^31 bases.
+// one can change, so err / CIGAR are written once, in order, as the walk proceeds: into the warp's staging rings
+// (WarpSmem::errb / cigb), from which complete 128-byte chunks leave for HBM.
+// All positions are 32-bit: the host refuses reads whose raw capacity reaches 2^30 bases.
 struct Stitch {
-  const uint8_t* raw;
-  uint8_t* err;
-  uint8_t* cig;
   uint32_t L;
-  uint32_t cap;
+  uint32_t cap;          // capacity of the read's err / CIGAR areas in HBM (multiple of CHUNK)
   uint32_t err_len, cig_len;
   uint32_t pos_in_raw;   // sequence(): end of the last emitted change
   uint32_t real_edit;
-  bool has_last, l_emit;
   uint32_t lb, le, lseq_len, ledit;
+  uint32_t flags;        // F_HAS_LAST | F_EMIT
   uint32_t status;
 };
+enum : uint32_t { F_HAS_LAST = 1u, F_EMIT = 2u };
 
-// Capacity is checked once per event by the caller (add_change) or by st_tail.
-__device__ __forceinline__ void st_emit_gap(Stitch& S, uint32_t n, int lane) {  // raw[pos_in_raw .. +n) copied, '=' in the CIGAR
-  const uint8_t* src = S.raw + S.pos_in_raw;
-  uint8_t* de = S.err + S.err_len;
-  uint8_t* dc = S.cig + S.cig_len;
-  if ((uint32_t)lane < n) {
-    de[lane] = src[lane];
-    dc[lane] = '=';
+__device__ __forceinline__ uint4 eq16() { return make_uint4(0x3d3d3d3du, 0x3d3d3d3du, 0x3d3d3d3du, 0x3d3d3d3du); }
+
+// Sends the chunks completed since (e_old, c_old) to HBM and re-arms the CIGAR ring with '='.  Both rings are indexed
+// by absolute position modulo RING, so a chunk is 128-byte aligned on both sides.  The capacity test lives here: a
+// read that comes within two chunks of its planned capacity is reported (the host re-plans the batch with more slack).
+__device__ __forceinline__ uint32_t flush_chunks(WarpSmem* ws, const ReadKernelParams& P, uint32_t ridx, uint32_t e_old, uint32_t e_new,
+                                                 uint32_t c_old, uint32_t c_new, uint32_t cap, int lane) {
+  __syncwarp();
+  const uint64_t off = P.out_off[ridx];
+  if (lane < 8) {
+    uint4* eg = reinterpret_cast<uint4*>(P.err + off);
+    uint4* cg = reinterpret_cast<uint4*>(P.cig + off);
+    for (uint32_t c = e_old & ~(CHUNK - 1u); c < (e_new & ~(CHUNK - 1u)); c += CHUNK)
+      eg[(c >> 4) + lane] = *reinterpret_cast<const uint4*>(&ws->errb[(c & (RING - 1u)) + 16u * lane]);
+    for (uint32_t c = c_old & ~(CHUNK - 1u); c < (c_new & ~(CHUNK - 1u)); c += CHUNK) {
+      uint4* sp = reinterpret_cast<uint4*>(&ws->cigb[(c & (RING - 1u)) + 16u * lane]);
+      cg[(c >> 4) + lane] = *sp;
+      *sp = eq16();
+    }
   }
-  for (uint32_t i = lane + 32; i < n; i += 32) {
-    de[i] = src[i];
-    dc[i] = '=';
-  }
-  S.err_len += n;
-  S.cig_len += n;
+  __syncwarp();
+  return (max(e_new, c_new) + 2u * CHUNK > cap) ? (uint32_t)ST_OUT_OVERFLOW : (uint32_t)ST_OK;
+}
+__device__ __noinline__ uint32_t flush_chunks_cold(WarpSmem* ws, const ReadKernelParams& P, uint32_t ridx, uint32_t e_old, uint32_t e_new,
+                                                   uint32_t c_old, uint32_t c_new, uint32_t cap, int lane) {
+  return flush_chunks(ws, P, ridx, e_old, e_new, c_old, c_new, cap, lane);
 }
 
-__device__ __forceinline__ void st_emit_seq(Stitch& S, const uint8_t* q, uint32_t n, int lane) {
-  uint8_t* de = S.err + S.err_len;
-  if ((uint32_t)lane < n) de[lane] = q[lane];
-  for (uint32_t i = lane + 32; i < n; i += 32) de[i] = q[i];
-  S.err_len += n;
+// Appends n positions to the stitch, at most 64 per step with a flush in between (cold path: long unchanged
+// stretches, glitch inserts, large alignments).  err_src != nullptr: those bytes go to the sequence; cig_src != nullptr:
+// those ops go to the CIGAR; cig_eq: the CIGAR advances over its '=' pre-fill instead.
+__device__ __forceinline__ void stitch_append(Stitch& S, WarpSmem* ws, const ReadKernelParams& P, uint32_t ridx, const uint8_t* err_src,
+                                              const uint8_t* cig_src, bool cig_eq, uint32_t n, int lane) {
+  for (uint32_t done = 0; done < n && S.status == ST_OK; done += 64) {
+    const uint32_t m = min(64u, n - done);
+    const uint32_t e_old = S.err_len, c_old = S.cig_len;
+    for (uint32_t i = lane; i < m; i += 32) {
+      if (err_src) ws->errb[(e_old + i) & (RING - 1u)] = err_src[done + i];
+      if (cig_src) ws->cigb[(c_old + i) & (RING - 1u)] = cig_src[done + i];
+    }
+    if (err_src) S.err_len += m;
+    if (cig_src || cig_eq) S.cig_len += m;
+    if (((e_old ^ S.err_len) | (c_old ^ S.cig_len)) >= CHUNK) S.status = flush_chunks(ws, P, ridx, e_old, S.err_len, c_old, S.cig_len, S.cap, lane);
+    __syncwarp();
+  }
 }
 
-// AbsChanges::add_change (src/simulate/error.rs:173-193) with contain / overlap / merge /
-// update_align (error.rs:83-164).  Returns the edit count to subtract from the target.
-// One alignment call site: the merge and the push cases only differ in which slices are aligned.
-// `fk` != 0 says that oseq is raw[ob..oe) with ONE random edit of kind fk (1 substitution, 2 insertion, 3 deletion) at
-// offset fep (random_error, src/model/error.rs:116-135).  When such a change is pushed, or merged into a last change
-// whose raw and err ends coincide, the piece that gets aligned is a k-mer tail against the same tail with at most one
-// edit, and the CIGAR of the reference's LCS alignment has a closed form, so no DP is run: the suffix after the edit
-// matches on the diagonal, the edit then slides left through equal neighbours (a match always takes the diagonal),
-// and where it stops the prefixes are identical, which forces X / I / D there.  Checked against the DP + tie-break
-// exhaustively for all k-mers up to k = 7 over 1-, 2- and 4-letter alphabets and for every piece offset (DESIGN.md).
-// fk == 4: oseq is alternative `fep` of the error-model table for the k-mer raw[ob..oe); its alignments against the key
-// (whole, and every tail piece) were computed at load time with the same rule, so they are copied instead of recomputed.
-__device__ __forceinline__ uint32_t add_change(Stitch& S, WarpSmem* ws, const ReadKernelParams& P, uint32_t gwarp, uint32_t ob, uint32_t oe,
-                                               const uint8_t* oseq, uint32_t olen, uint32_t fk, uint32_t fep, int lane) {
-  bool merge = false, piece_fast = fk != 0;  // closed form applies to a pushed change, and to some merges (below)
-  uint32_t es = 0, rs, re;
-  if (S.has_last) {
+// The bookkeeping half of AbsChanges::add_change (src/simulate/error.rs:173-193) with contain / overlap / merge /
+// update_align (error.rs:83-164): decides what happens to a change [ob, oe) carrying olen bytes and updates the state
+// of `changes.last()`.  What is left to the caller is to append the piece bytes [es, olen) after `gap` unchanged
+// bases, and to align them against raw[rs, re).
+struct ChangePlan {
+  uint32_t es, rs, re, gap, gap_src;
+  bool contained, fast;
+};
+// `fk` != 0 says that the piece is raw[ob..oe) with ONE random edit of kind fk (1 substitution, 2 insertion, 3 deletion)
+// at offset fep (random_error, src/model/error.rs:116-135), or (fk == 4) alternative `fep` of the error-model table for
+// the k-mer raw[ob..oe).  `fast` comes back true when the piece that gets aligned is a k-mer tail against the same tail:
+// a pushed change, or a merge into a last change whose raw and err ends coincide.  Then the CIGAR of the reference's LCS
+// alignment has a closed form (single edit) or was computed at load time (table), and no DP is run.
+__device__ __forceinline__ ChangePlan plan_change(Stitch& S, uint32_t ob, uint32_t oe, uint32_t olen, uint32_t fk) {
+  ChangePlan c;
+  c.es = 0;
+  c.gap = 0;
+  c.gap_src = S.pos_in_raw;
+  c.contained = false;
+  c.fast = fk != 0;
+  c.rs = c.re = 0;
+  bool merge = false;
+  if (S.flags & F_HAS_LAST) {
     const uint32_t l_end_err = S.lb + S.lseq_len;
-    if (oe <= l_end_err || oe <= S.le || ob + olen <= l_end_err) return 0;  // contain (error.rs:83-88)
-    if (ob < l_end_err || ob < S.le) {                                       // overlap -> merge (error.rs:105-152)
+    if (oe <= l_end_err || oe <= S.le || ob + olen <= l_end_err) {  // contain (error.rs:83-88)
+      c.contained = true;
+      return c;
+    }
+    if (ob < l_end_err || ob < S.le) {  // overlap -> merge (error.rs:105-152)
       merge = true;
       const uint32_t old_end = S.le;
       if (ob < l_end_err) {
-        es = l_end_err - ob;  // olen > es holds because the change is not contained
-        S.le = S.le + oe - ob - es;
+        c.es = l_end_err - ob;  // olen > es holds because the change is not contained
+        S.le = S.le + oe - ob - c.es;
         // If the last change consumed as many raw bases as it produced (old_end == l_end_err), the appended piece
-        // oseq[es..] faces exactly raw[ob + es .. oe): the same k-mer tail, so the single-edit closed form still holds.
-        piece_fast = piece_fast && old_end == l_end_err && es <= oe - ob;  // (a longer overlap makes the raw slice run backwards)
+        // oseq[es..] faces exactly raw[ob + es .. oe): the same k-mer tail.  (A longer overlap makes the raw slice run backwards.)
+        c.fast = c.fast && old_end == l_end_err && c.es <= oe - ob;
       } else {
         S.le = ob + olen;
-        piece_fast = false;
+        c.fast = false;
       }
       if (S.le < S.L - 1) {
-        if (old_end < S.le) { rs = old_end; re = S.le; } else { rs = S.le; re = old_end; }
-      } else { rs = old_end; re = S.L; piece_fast = false; }
-      if (rs > re || re > S.L || es > olen) { S.status = ST_REF_PANIC; return 0; }
-      S.lseq_len += olen - es;
+        if (old_end < S.le) { c.rs = old_end; c.re = S.le; } else { c.rs = S.le; c.re = old_end; }
+      } else { c.rs = old_end; c.re = S.L; c.fast = false; }
+      if (c.rs > c.re || c.re > S.L || c.es > olen) { S.status = ST_REF_PANIC; c.contained = true; return c; }
+      S.lseq_len += olen - c.es;
     }
   }
-  uint32_t gap = 0;
   if (!merge) {  // push a new change (update_align: error.rs:155-164)
-    if (S.has_last && S.l_emit) {  // the previous change is final: sequence() accounts for it
+    if ((S.flags & (F_HAS_LAST | F_EMIT)) == (F_HAS_LAST | F_EMIT)) {  // the previous change is final: sequence() accounts for it
       S.real_edit += S.ledit;
       S.pos_in_raw = S.le;
     }
-    rs = ob;
-    re = oe > S.L ? S.L : oe;
-    if (rs > re) { S.status = ST_REF_PANIC; return 0; }
-    S.has_last = true;
-    S.l_emit = ob >= S.pos_in_raw;  // sequence(): `if change.begin() < pos_in_raw { continue }`
+    c.rs = ob;
+    c.re = oe > S.L ? S.L : oe;
+    if (c.rs > c.re) { S.status = ST_REF_PANIC; c.contained = true; return c; }
+    S.flags = F_HAS_LAST | (ob >= S.pos_in_raw ? F_EMIT : 0u);  // sequence(): `if change.begin() < pos_in_raw { continue }`
     S.lb = ob;
     S.le = oe;
     S.lseq_len = olen;
     S.ledit = 0;
-    gap = ob - S.pos_in_raw;  // only meaningful when l_emit
+    c.gap_src = S.pos_in_raw;
+    c.gap = ob - S.pos_in_raw;  // only meaningful when F_EMIT
   }
-  const uint32_t add = olen - es, tn = re - rs;
-  uint8_t* dst = nullptr;
-  if (S.l_emit) {
-    // one capacity check per event: the CIGAR of this piece has at most add + tn ops
-    if (S.err_len + gap + add > S.cap || S.cig_len + gap + add + tn > S.cap) { S.status = ST_OUT_OVERFLOW; return 0; }
-    if (gap) st_emit_gap(S, gap, lane);
-    st_emit_seq(S, oseq + es, add, lane);
-    dst = S.cig + S.cig_len;
+  return c;
+}
+
+// Cold form of add_change: the piece lives in memory (glitch inserts, table alternatives longer than a warp).
+struct ColdOut {
+  Stitch S;
+  uint32_t edits;
+};
+__device__ __noinline__ ColdOut add_change_cold(Stitch S, WarpSmem* ws, const ReadKernelParams& P, uint32_t gwarp, uint32_t ridx, const uint8_t* raw,
+                                                uint32_t ob, uint32_t oe, const uint8_t* oseq, uint32_t olen, int lane) {
+  ColdOut o;
+  o.edits = 0;
+  const ChangePlan c = plan_change(S, ob, oe, olen, 0);
+  if (!c.contained) {
+    const uint32_t add = olen - c.es, tn = c.re - c.rs;
+    const bool emit = (S.flags & F_EMIT) != 0;
+    uint8_t* fwd = P.sc_ops + (uint64_t)gwarp * P.sc_ops_cap + P.sc_ops_cap / 2;  // ops in forward order (second half of the scratch)
+    if (emit) {
+      if (c.gap) stitch_append(S, ws, P, ridx, raw + c.gap_src, nullptr, true, c.gap, lane);
+      stitch_append(S, ws, P, ridx, oseq + c.es, nullptr, false, add, lane);
+    }
+    __syncwarp();
+    const uint64_t a = warp_align(ws, P, gwarp, oseq + c.es, add, raw + c.rs, tn, emit ? fwd : nullptr, lane);
+    __syncwarp();
+    if (align_status(a)) S.status = align_status(a);
+    else {
+      if (emit && S.status == ST_OK) stitch_append(S, ws, P, ridx, nullptr, fwd, false, align_nops(a), lane);
+      S.ledit += align_edits(a);
+      o.edits = align_edits(a);
+    }
   }
-  if (piece_fast && fk == 4) {
+  o.S = S;
+  return o;
+}
+
+// Cold appends from the hot form of add_change: a long unchanged stretch raw[src, src + n) (err_src, the CIGAR advances
+// over its '=' pre-fill), or the ops of a large alignment (cig_src).  The lengths travel by value.
+struct AppendOut {
+  uint32_t err_len, cig_len, status;
+};
+__device__ __noinline__ AppendOut append_cold(WarpSmem* ws, const ReadKernelParams& P, uint32_t ridx, const uint8_t* err_src, const uint8_t* cig_src,
+                                              uint32_t n, uint32_t err_len, uint32_t cig_len, uint32_t cap, int lane) {
+  Stitch S;
+  S.err_len = err_len;
+  S.cig_len = cig_len;
+  S.cap = cap;
+  S.status = ST_OK;
+  stitch_append(S, ws, P, ridx, err_src, cig_src, cig_src == nullptr, n, lane);
+  AppendOut g;
+  g.err_len = S.err_len;
+  g.cig_len = S.cig_len;
+  g.status = S.status;
+  return g;
+}
+
+// Alignment of a register-resident piece that the register aligner cannot take (window wider than a warp, or a byte
+// outside ACGT): the piece goes through shared memory to the general aligners.  Returns the packed alignment result;
+// the ops are left in forward order in the second half of the warp's op scratch.
+__device__ __noinline__ uint64_t align_piece_cold(WarpSmem* ws, const ReadKernelParams& P, uint32_t gwarp, uint32_t c, uint32_t es, uint32_t olen,
+                                                  const uint8_t* t, uint32_t tn, bool emit, int lane) {
+  __syncwarp();
+  if ((uint32_t)lane < olen) ws->alt[lane] = (uint8_t)c;  // olen <= 32
+  __syncwarp();
+  uint8_t* fwd = P.sc_ops + (uint64_t)gwarp * P.sc_ops_cap + P.sc_ops_cap / 2;
+  const uint64_t a = warp_align(ws, P, gwarp, ws->alt + es, olen - es, t, tn, emit ? fwd : nullptr, lane);
+  __syncwarp();
+  return a;
+}
+
+// Hot form of add_change: the piece (olen <= 32 bytes) lives in registers, lane i holding byte i in `c`; `kb` holds the
+// k-mer raw[ob + lane] it replaces.  Returns the edit count to subtract from the target.
+//
+// Closed form for a single random edit (fast, fk 1..3), in k-mer coordinates (piece offset j = lane - es): walking the
+// reference's traceback from the end, the common suffix after the edit is taken on the diagonal (a match always wins the
+// tie-break), the edit then slides left while the neighbouring bases are equal (still matches), and where it stops the
+// two prefixes are identical, which forces X / I / D there and '=' before it.  Checked against the DP + tie-break
+// exhaustively for all k-mers up to k = 7 over 1-, 2- and 4-letter alphabets and for every piece offset (DESIGN.md).
+__device__ __forceinline__ uint32_t add_change_reg(Stitch& S, WarpSmem* ws, const ReadKernelParams& P, uint32_t gwarp, uint32_t ridx, const uint8_t* raw,
+                                                   uint32_t ob, uint32_t oe, uint32_t c, uint32_t olen, uint32_t fk, uint32_t fep, uint32_t kb,
+                                                   int lane) {
+  const ChangePlan cp = plan_change(S, ob, oe, olen, fk);
+  if (cp.contained) return 0;
+  const uint32_t es = cp.es, add = olen - es, tn = cp.re - cp.rs;
+  const bool emit = (S.flags & F_EMIT) != 0;
+  uint32_t e_old = S.err_len, c_old = S.cig_len;  // where the flush at the end of this event starts
+  if (emit) {
+    if (cp.gap) {
+      if (cp.gap <= 32u) {
+        if ((uint32_t)lane < cp.gap) ws->errb[(S.err_len + lane) & (RING - 1u)] = raw[cp.gap_src + lane];
+        S.err_len += cp.gap;
+        S.cig_len += cp.gap;  // the CIGAR ring is pre-filled with '='
+      } else {
+        const AppendOut g = append_cold(ws, P, ridx, raw + cp.gap_src, nullptr, cp.gap, S.err_len, S.cig_len, S.cap, lane);
+        e_old = S.err_len = g.err_len;  // append_cold has flushed its own chunks
+        c_old = S.cig_len = g.cig_len;
+        if (g.status) { S.status = g.status; return 0; }
+      }
+    }
+    if ((uint32_t)lane >= es && (uint32_t)lane < olen) ws->errb[(S.err_len + lane - es) & (RING - 1u)] = (uint8_t)c;
+    S.err_len += add;
+  }
+  uint32_t ed, nops;
+  if (cp.fast && fk == 4) {  // table alternative against its own key: alignments precomputed at load time
     const DeviceModels& M = P.M;
     const uint32_t pi = M.em_piece_begin[fep] + es;
-    const uint32_t o0 = M.em_piece_off[pi], total = M.em_piece_off[pi + 1] - o0;
-    const uint32_t ed = M.em_piece_edits[pi];
-    if (dst) for (uint32_t x = lane; x < total; x += 32) dst[x] = M.em_piece_ops[o0 + x];
-    if (S.l_emit) S.cig_len += total;
-    S.ledit += ed;
-    return ed;
-  }
-  if (piece_fast) {
-    const uint8_t* q = oseq + es;
-    const uint8_t* t = S.raw + rs;
+    const uint32_t o0 = M.em_piece_off[pi];
+    nops = M.em_piece_off[pi + 1] - o0;
+    ed = M.em_piece_edits[pi];
+    if (emit) for (uint32_t x = lane; x < nops; x += 32) ws->cigb[(S.cig_len + x) & (RING - 1u)] = M.em_piece_ops[o0 + x];
+  } else if (cp.fast) {
     const uint32_t e = fep >= es ? fep - es : 0;    // where the edit sits inside the piece (an edit left of it acts at 0)
     const bool has_edit = !(fk == 1 && fep < es);   // a substitution in the overlapped part leaves the piece identical
     uint32_t at = e;                                // where the non-'=' op lands
     if (fk != 1) {
       // slide left while the base left of the edit equals the one it would be swapped with
-      const bool c = (uint32_t)lane >= 1 && (uint32_t)lane <= e && (fk == 2 ? q[lane] == t[lane - 1] : t[lane - 1] == t[lane]);
-      const uint32_t B = __ballot_sync(0xffffffffu, c);
+      const uint32_t kprev = __shfl_up_sync(0xffffffffu, kb, 1);
+      const bool sl = (uint32_t)lane > es && (uint32_t)lane <= es + e && (fk == 2 ? c == kprev : kb == kprev);
+      const uint32_t B = __ballot_sync(0xffffffffu, sl) >> es;
       at = e - __clz(~(B << (31 - e)));
     }
-    const uint32_t total = fk == 2 ? add : tn;  // substitution / deletion: one op per raw base, insertion: one per piece base
-    if (dst && (uint32_t)lane < total) dst[lane] = (has_edit && (uint32_t)lane == at) ? (fk == 1 ? 'X' : fk == 2 ? 'I' : 'D') : '=';
-    if (S.l_emit) S.cig_len += total;
-    const uint32_t ed = has_edit ? 1u : 0u;
-    S.ledit += ed;
-    return ed;
+    nops = fk == 2 ? add : tn;  // substitution / deletion: one op per raw base, insertion: one per piece base
+    ed = has_edit ? 1u : 0u;
+    if (emit && has_edit) ws->cigb[(S.cig_len + at) & (RING - 1u)] = fk == 1 ? 'X' : fk == 2 ? 'I' : 'D';
+  } else if ((add == 0 || tn == 0) && add + tn <= 32u) {  // all deletions / all insertions
+    nops = add + tn;
+    ed = nops;
+    if (emit && (uint32_t)lane < nops) ws->cigb[(S.cig_len + lane) & (RING - 1u)] = add == 0 ? 'D' : 'I';
+  } else {
+    uint64_t a = ~0ULL;
+    if (tn <= 32u && add <= 31u && add != 0 && tn != 0) {
+      const uint32_t qc = __shfl_sync(0xffffffffu, c, (lane - 1 + (int)es) & 31);
+      const uint32_t tc = (uint32_t)lane < tn ? raw[cp.rs + lane] : (uint32_t)'A';
+      a = warp_align_regs<true>(qc, add, tc, tn, emit ? ws->cigb : nullptr, S.cig_len, lane);
+    }
+    if (a == ~0ULL) {  // window wider than a warp or a byte outside ACGT: general aligners, ops through the scratch
+      a = align_piece_cold(ws, P, gwarp, c, es, olen, raw + cp.rs, tn, emit, lane);
+      if (align_status(a)) { S.status = align_status(a); return 0; }
+      if (emit) {
+        // flush what this event staged so far, then append the ops (possibly more than a ring's worth)
+        if (((e_old ^ S.err_len) | (c_old ^ S.cig_len)) >= CHUNK) S.status = flush_chunks_cold(ws, P, ridx, e_old, S.err_len, c_old, S.cig_len, S.cap, lane);
+        const uint8_t* fwd = P.sc_ops + (uint64_t)gwarp * P.sc_ops_cap + P.sc_ops_cap / 2;
+        const AppendOut g = append_cold(ws, P, ridx, nullptr, fwd, align_nops(a), S.err_len, S.cig_len, S.cap, lane);
+        S.cig_len = g.cig_len;
+        if (g.status) S.status = g.status;
+      }
+      S.ledit += align_edits(a);
+      return align_edits(a);
+    }
+    nops = align_nops(a);
+    ed = align_edits(a);
   }
-  const uint64_t a = warp_align(ws, P, gwarp, oseq + es, add, S.raw + rs, tn, dst, lane);
-  if (align_status(a)) { S.status = align_status(a); return 0; }
-  if (S.l_emit) S.cig_len += align_nops(a);
-  S.ledit += align_edits(a);
-  return align_edits(a);
+  if (emit) {
+    S.cig_len += nops;
+    if (((e_old ^ S.err_len) | (c_old ^ S.cig_len)) >= CHUNK) {
+      const uint32_t st = flush_chunks_cold(ws, P, ridx, e_old, S.err_len, c_old, S.cig_len, S.cap, lane);
+      if (st) S.status = st;
+    }
+  }
+  S.ledit += ed;
+  return ed;
 }
 
 __device__ __forceinline__ void process_read(const ReadKernelParams& P, WarpSmem* ws, uint32_t gwarp, uint32_t ridx, int lane) {
@@ -347,23 +490,19 @@ __device__ __forceinline__ void process_read(const ReadKernelParams& P, WarpSmem
   const uint32_t L = (uint32_t)so.value;
 
   Stitch S;
-  S.raw = raw;
   S.L = L;
-  S.err = P.err + P.out_off[ridx];
-  S.cig = P.cig + P.out_off[ridx];
   S.cap = (uint32_t)(P.out_off[ridx + 1] - P.out_off[ridx]);
   S.err_len = S.cig_len = 0;
   S.pos_in_raw = 0;
   S.real_edit = 0;
-  S.has_last = false;
-  S.l_emit = false;
+  S.flags = 0;
   S.lb = S.le = S.lseq_len = S.ledit = 0;
   S.status = ST_OK;
+  if (lane < (int)(RING / 16)) *reinterpret_cast<uint4*>(&ws->cigb[16 * lane]) = eq16();
+  __syncwarp();
 
   // ---- K3: error::sequence (src/simulate/error.rs:201-217) ----
   double target = (1.0 - P.descs[ridx].identity) * (double)L;  // number_of_edit, error.rs:196-198
-  const GlitchRec* grec = P.sc_grec + (uint64_t)gwarp * P.sc_grec_cap;
-  const uint8_t* gseq = P.sc_gseq + (uint64_t)gwarp * P.sc_gseq_cap;
   uint32_t ng = 0;
   if (M.has_distance) {
     so = stage_glitches(rng, P, gwarp, L);
@@ -378,10 +517,10 @@ __device__ __forceinline__ void process_read(const ReadKernelParams& P, WarpSmem
     const uint32_t nlim = L - k;
     uint32_t pos = 0;
     uint32_t g = 0;
-    uint32_t gbegin = ng ? (uint32_t)grec[0].begin : ~0u;
+    uint32_t gbegin = ng ? (uint32_t)P.sc_grec[(uint64_t)gwarp * P.sc_grec_cap].begin : ~0u;
     bool glitch_checked = false;
     while (pos < nlim) {
-      rng.need(64);
+      rng.need(64 + 32);  // 64 words for the 32 positions + spare for the draws of the event (WarpRng hot draws)
       const uint32_t pi = pos + (uint32_t)lane;
       const bool inb = pi < nlim;
       const double rem = (double)(L - pi);
@@ -407,29 +546,28 @@ __device__ __forceinline__ void process_read(const ReadKernelParams& P, WarpSmem
         glitch_checked = false;
       }
       if (!(ff & 1u)) break;  // pos == L - k
-      uint32_t ob, oe, olen, fk = 0, fep = 0;
-      const uint8_t* oseq;
+      uint32_t edits;
       const bool is_glitch = (ff & 2u) != 0;
       if (is_glitch) {  // glitch due at pos (error.rs:282-287)
+        const GlitchRec* grec = P.sc_grec + (uint64_t)gwarp * P.sc_grec_cap;
         const GlitchRec gr = grec[g];
-        ob = (uint32_t)gr.begin;
-        oe = (uint32_t)gr.end;
-        oseq = gseq + gr.seq_off;
-        olen = gr.seq_len;
         ++g;
         gbegin = (g < ng) ? (uint32_t)grec[g].begin : ~0u;
+        const ColdOut co = add_change_cold(S, ws, P, gwarp, ridx, raw, (uint32_t)gr.begin, (uint32_t)gr.end,
+                                           P.sc_gseq + (uint64_t)gwarp * P.sc_gseq_cap + gr.seq_off, gr.seq_len, lane);
+        S = co.S;
+        edits = co.edits;
       } else {
         if (ff & 4u) break;  // error.rs:289-291
         if (!(ff & 8u)) rng.off += 2;
-        // Error::add_errors_to_kmer (src/model/error.rs:93-107) -> ws->alt
-        const uint8_t* kmer = raw + pos;
+        // Error::add_errors_to_kmer (src/model/error.rs:93-107): the altered k-mer is built in registers, lane i = byte i
+        const uint32_t kb = (uint32_t)lane < k ? (uint32_t)raw[pos + lane] : 0u;
+        uint32_t c = 0, olen, fk, fep;
         int key = -1;
-        __syncwarp();
         if (M.em_index) {  // 2-bit code of the k-mer; any byte outside ACGT misses the table
           uint32_t part = 0, bad = 0;
           if ((uint32_t)lane < k) {
-            uint8_t c = kmer[lane];
-            uint32_t s = c == 'A' ? 0u : c == 'C' ? 1u : c == 'G' ? 2u : c == 'T' ? 3u : 4u;
+            uint32_t s = kb == 'A' ? 0u : kb == 'C' ? 1u : kb == 'G' ? 2u : kb == 'T' ? 3u : 4u;
             bad = s > 3u;
             part = (s & 3u) << (2 * (k - 1 - lane));
           }
@@ -437,36 +575,47 @@ __device__ __forceinline__ void process_read(const ReadKernelParams& P, WarpSmem
           if (!__any_sync(0xffffffffu, bad)) key = M.em_index[code];
         }
         if (key >= 0) {
-          so = stage_alt_from_table(rng, M, ws, key);
+          so = stage_alt_from_table(rng, M, key);
           rng.set_cursor(so.base, so.cur);
           olen = (uint32_t)so.value;
           fk = 4;
           fep = so.status;
-        } else {  // random_error (src/model/error.rs:116-135)
-          const uint32_t ep = (uint32_t)rng.gen_range_u64(0, k - 1);
-          const uint32_t kind = rng.gen_range_u32(1, 3);  // 1 substitution, 2 insertion, 3 deletion
-          uint8_t nb = 0;
-          if (kind == 1) nb = rng.random_base_diff(kmer[ep]);
-          else if (kind == 2) nb = rng.random_base();
-          const uint32_t n = kind == 1 ? k : (kind == 2 ? k + 1 : k - 1);
-          if ((uint32_t)lane < n) {
-            const uint32_t i = lane;
-            uint8_t c;
-            if (kind == 1) c = (i == ep) ? nb : kmer[i];
-            else if (kind == 2) c = (i < ep) ? kmer[i] : (i == ep ? nb : kmer[i - 1]);
-            else c = (i < ep) ? kmer[i] : kmer[i + 1];
-            ws->alt[i] = c;
+          const uint32_t o0 = M.em_alt_off[fep];
+          if (olen <= 32u) {
+            if ((uint32_t)lane < olen) c = M.em_alt_bytes[o0 + lane];
+          } else {  // an alternative longer than a warp: through memory
+            const ColdOut co = add_change_cold(S, ws, P, gwarp, ridx, raw, pos, pos + k, M.em_alt_bytes + o0, olen, lane);
+            S = co.S;
+            target -= (double)co.edits;
+            if (S.status) break;
+            if (target < 0.0 || target > (double)(L - pos)) break;  // error.rs:298-300
+            pos += 1;
+            glitch_checked = false;
+            continue;
           }
-          __syncwarp();
-          olen = n;
+        } else {  // random_error (src/model/error.rs:116-135)
+          const uint32_t ep = rng.gen_index_hot(k);
+          const uint32_t kind = rng.gen_range_u32_hot(1, 3);  // 1 substitution, 2 insertion, 3 deletion
+          if (kind == 1) {
+            const uint32_t nb = rng.random_base_diff_hot(__shfl_sync(0xffffffffu, kb, ep));
+            c = (uint32_t)lane == ep ? nb : kb;
+            olen = k;
+          } else if (kind == 2) {
+            const uint32_t nb = rng.random_base_diff_hot(256u);
+            const uint32_t kprev = __shfl_up_sync(0xffffffffu, kb, 1);
+            c = (uint32_t)lane < ep ? kb : ((uint32_t)lane == ep ? nb : kprev);
+            olen = k + 1;
+          } else {
+            const uint32_t knext = __shfl_down_sync(0xffffffffu, kb, 1);
+            c = (uint32_t)lane < ep ? kb : knext;
+            olen = k - 1;
+          }
           fk = kind;
           fep = ep;
         }
-        ob = pos;
-        oe = pos + k;
-        oseq = ws->alt;
+        edits = add_change_reg(S, ws, P, gwarp, ridx, raw, pos, pos + k, c, olen, fk, fep, kb, lane);
       }
-      target -= (double)add_change(S, ws, P, gwarp, ob, oe, oseq, olen, fk, fep, lane);
+      target -= (double)edits;
       if (S.status) break;
       if (is_glitch) {
         glitch_checked = true;  // same pos again, with the new target, glitch check done
@@ -480,15 +629,19 @@ __device__ __forceinline__ void process_read(const ReadKernelParams& P, WarpSmem
 
   // ---- K5: tail of the stitch (error.rs:241-246) ----
   if (S.status == ST_OK) {
-    if (S.has_last && S.l_emit) {
+    if ((S.flags & (F_HAS_LAST | F_EMIT)) == (F_HAS_LAST | F_EMIT)) {
       S.real_edit += S.ledit;
       S.pos_in_raw = S.le;
     }
     if (S.pos_in_raw < L) {
-      const uint32_t n = L - S.pos_in_raw;
-      if (S.err_len + n > S.cap || S.cig_len + n > S.cap) S.status = ST_OUT_OVERFLOW;
-      else st_emit_gap(S, n, lane);
+      const AppendOut gpo = append_cold(ws, P, ridx, raw + S.pos_in_raw, nullptr, L - S.pos_in_raw, S.err_len, S.cig_len, S.cap, lane);
+      S.err_len = gpo.err_len;
+      S.cig_len = gpo.cig_len;
+      S.status = gpo.status;
     }
+    // the partial last chunks (the chunk past max(len) stays inside the capacity: see flush_chunks)
+    const uint32_t st = flush_chunks_cold(ws, P, ridx, S.err_len, S.err_len + CHUNK, S.cig_len, S.cig_len + CHUNK, ~0u, lane);
+    (void)st;
   }
   __syncwarp();
   if (lane == 0) {
@@ -503,7 +656,9 @@ __device__ __forceinline__ void process_read(const ReadKernelParams& P, WarpSmem
 
 __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, RR_BLOCKS_PER_SM) rr_read_kernel(const __grid_constant__ ReadKernelParams P) {
   __shared__ WarpSmem smem[WARPS_PER_BLOCK];
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  int lane;
+  asm volatile("mov.u32 %0, %%laneid;" : "=r"(lane));  // volatile: kept in a register instead of being re-read from SR_TID at every use
   const uint32_t gwarp = blockIdx.x * WARPS_PER_BLOCK + warp;
   WarpSmem* ws = &smem[warp];
   for (;;) {

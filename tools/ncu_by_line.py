@@ -48,6 +48,17 @@ for name, ins in secs:
         r = data[pos + j]; e = int(r[ie]); s = int(r[isamp])
         agg[ln][0] += e; agg[ln][1] += s; agg[ln][2] += 1
         fn[name][0] += e; fn[name][1] += s; fn[name][2] += 1
+if os.environ.get("LISTING"):  # annotated SASS listing: executions per SASS instruction, source line, opcode text
+    with open(os.environ["LISTING"], "w") as f:
+        for name, ins in secs:
+            if len(ins) < 8: continue
+            sig = [x[0].split(" ")[0] for x in ins[:12]]
+            for p in range(0, len(ncu_ops) - len(ins) + 1):
+                if [o.split(" ")[0] for o in ncu_ops[p:p + 12]] == sig:
+                    for j, (op, ln) in enumerate(ins):
+                        r = data[p + j]
+                        f.write("%6d %12d %7d  %-22s %5d  %s\n" % (j, int(r[ie]), int(r[isamp]), ln[0] if ln else "?", ln[1] if ln else 0, r[isrc].strip()))
+                    break
 print("ncu rows %d mapped %d ; total executed %d samples %d" % (len(data), used, tot_e, tot_s))
 for k, v in sorted(fn.items(), key=lambda x: -x[1][0]):
     print("FUNC %-90s exec %5.2f%% samples %5.2f%% sass %d" % (k[:90], 100 * v[0] / tot_e, 100 * v[1] / tot_s, v[2]))
