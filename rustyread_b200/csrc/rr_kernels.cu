@@ -834,11 +834,10 @@ RR_API int rr_debug_align(rr_ctx* ctx, const uint8_t* query, uint32_t m, const u
 }
 
 __global__ void rr_debug_rng_kernel(uint64_t seed, uint64_t first, uint32_t n, uint32_t* out) {
-  __shared__ uint32_t words[RNG_WORDS + 8];
+  __shared__ WarpSmem ws;
   WarpRng rng;
-  rng.seed(seed, words, threadIdx.x & 31);
-  rng.set_cursor(rng.base, first);
-  rng.refill();
+  rng.seed(seed, &ws, threadIdx.x & 31);
+  rng.seek(first);
   for (uint32_t i = 0; i < n; ++i) {
     uint32_t v = rng.next_u32();
     if (threadIdx.x == 0) out[i] = v;

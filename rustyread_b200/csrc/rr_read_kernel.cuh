@@ -5,11 +5,18 @@
 
 namespace rr {
 
-// What an out-of-line stage hands back: the generator state (kept in registers by the caller) + one value.
+// What an out-of-line stage hands back: the generator's offset (its base lives in shared memory) + one value.
 struct StageOut {
-  uint64_t base, cur, value;
-  uint32_t status;
+  uint64_t value;
+  uint32_t off, status;
 };
+__device__ __forceinline__ WarpRng stage_rng(uint32_t ws32, uint32_t off, int lane) {
+  WarpRng rng;
+  rng.ws = smem_ptr(ws32);
+  rng.off = off;
+  rng.lane = lane;
+  return rng;
+}
 
 __device__ __forceinline__ uint8_t complement(uint8_t c) {
   // bio::alphabets::dna::complement (IUPAC aware, case preserving); used by Reference::new (src/references.rs:27)
@@ -101,9 +108,10 @@ __device__ __forceinline__ uint64_t add_fragment(WarpRng& rng, const DeviceModel
 }
 
 // ---- K2 (out of line): the raw fragment of generate_read, src/simulate/mod.rs:243-271.  value = raw length ----
-__device__ __noinline__ StageOut stage_assemble(WarpRng rng, const ReadKernelParams& P, WarpSmem* ws, uint32_t ridx, uint8_t* raw) {
+__device__ __noinline__ StageOut stage_assemble(uint32_t ws32, uint32_t off, int lane, const ReadKernelParams& P, uint32_t ridx, uint8_t* raw) {
   const DeviceModels& M = P.M;
-  const int lane = rng.lane;
+  WarpRng rng = stage_rng(ws32, off, lane);
+  WarpSmem* ws = rng.ws;
   const rr_desc d = P.descs[ridx];
   const uint32_t k = M.k;
   uint64_t L = 0;
@@ -121,8 +129,7 @@ __device__ __noinline__ StageOut stage_assemble(WarpRng rng, const ReadKernelPar
   L += k;
   __syncwarp();
   StageOut o;
-  o.base = rng.base;
-  o.cur = rng.cursor();
+  o.off = rng.off;
   o.value = L;
   o.status = ST_OK;
   return o;
@@ -130,9 +137,9 @@ __device__ __noinline__ StageOut stage_assemble(WarpRng rng, const ReadKernelPar
 
 // ---- add_glitches (out of line), src/simulate/error.rs:250-264: positions, skips and inserted bases are drawn up front.
 // value = number of glitches recorded in the warp's scratch ----
-__device__ __noinline__ StageOut stage_glitches(WarpRng rng, const ReadKernelParams& P, uint32_t gwarp, uint64_t L) {
+__device__ __noinline__ StageOut stage_glitches(uint32_t ws32, uint32_t off, int lane, const ReadKernelParams& P, uint32_t gwarp, uint64_t L) {
   const DeviceModels& M = P.M;
-  const int lane = rng.lane;
+  WarpRng rng = stage_rng(ws32, off, lane);
   GlitchRec* grec = P.sc_grec + (uint64_t)gwarp * P.sc_grec_cap;
   uint8_t* gseq = P.sc_gseq + (uint64_t)gwarp * P.sc_gseq_cap;
   uint32_t ng = 0, status = ST_OK;
@@ -159,8 +166,7 @@ __device__ __noinline__ StageOut stage_glitches(WarpRng rng, const ReadKernelPar
   }
   __syncwarp();
   StageOut o;
-  o.base = rng.base;
-  o.cur = rng.cursor();
+  o.off = rng.off;
   o.value = ng;
   o.status = status;
   return o;
@@ -169,8 +175,8 @@ __device__ __noinline__ StageOut stage_glitches(WarpRng rng, const ReadKernelPar
 // Error::add_errors_to_kmer on a k-mer that is in the table (src/model/error.rs:96-100): one WeightedIndex draw.
 // Out of line: only file models reach it.  value = alternative length, status = global id of the chosen alternative
 // (it indexes em_alt_off and the precomputed alignments).
-__device__ __noinline__ StageOut stage_alt_from_table(WarpRng rng, const DeviceModels& M, int key) {
-  const int lane = rng.lane;
+__device__ __noinline__ StageOut stage_alt_from_table(uint32_t ws32, uint32_t off, int lane, const DeviceModels& M, int key) {
+  WarpRng rng = stage_rng(ws32, off, lane);
   uint32_t a0 = M.em_alt_begin[key], a1 = M.em_alt_begin[key + 1];
   uint32_t na = a1 - a0;
   double chosen = u64_to_unit12(rng.next_u64()) * M.em_scale[key] + 0.0;
@@ -181,8 +187,7 @@ __device__ __noinline__ StageOut stage_alt_from_table(WarpRng rng, const DeviceM
     idx += __popc(__ballot_sync(0xffffffffu, le));
   }
   StageOut o;
-  o.base = rng.base;
-  o.cur = rng.cursor();
+  o.off = rng.off;
   o.value = M.em_alt_off[a0 + idx + 1] - M.em_alt_off[a0 + idx];
   o.status = a0 + idx;
   return o;
@@ -193,17 +198,22 @@ __device__ __noinline__ StageOut stage_alt_from_table(WarpRng rng, const DeviceM
 // one can change, so err / CIGAR are written once, in order, as the walk proceeds: into the warp's staging rings
 // (WarpSmem::errb / cigb), from which complete 128-byte chunks leave for HBM.
 // All positions are 32-bit: the host refuses reads whose raw capacity reaches 2^30 bases.
+// The hot loop keeps this in registers, so it is kept small: the last change is (le = its end in raw, lee = its end in
+// err coordinates = begin + seq.len(), ledit); L, the capacity and the glitch cursor live in WarpSmem::st.
 struct Stitch {
-  uint32_t L;
-  uint32_t cap;          // capacity of the read's err / CIGAR areas in HBM (multiple of CHUNK)
   uint32_t err_len, cig_len;
   uint32_t pos_in_raw;   // sequence(): end of the last emitted change
   uint32_t real_edit;
-  uint32_t lb, le, lseq_len, ledit;
-  uint32_t flags;        // F_HAS_LAST | F_EMIT
-  uint32_t status;
+  uint32_t le, lee, ledit;
+  uint32_t flags;        // F_HAS_LAST | F_EMIT | F_GLITCH_CHECKED | status << 8
 };
-enum : uint32_t { F_HAS_LAST = 1u, F_EMIT = 2u };
+enum : uint32_t { F_HAS_LAST = 1u, F_EMIT = 2u, F_GLITCH_CHECKED = 4u, F_STATUS_SHIFT = 8u };
+enum : int { ST_L = 0, ST_CAP = 1, ST_G = 12, ST_NG = 13 };  // WarpSmem::st slots that are not Stitch fields
+
+__device__ __forceinline__ uint32_t st_status(const Stitch& S) { return S.flags >> F_STATUS_SHIFT; }
+__device__ __forceinline__ void st_fail(Stitch& S, uint32_t status) {
+  if (status && !st_status(S)) S.flags |= status << F_STATUS_SHIFT;
+}
 
 __device__ __forceinline__ uint4 eq16() { return make_uint4(0x3d3d3d3du, 0x3d3d3d3du, 0x3d3d3d3du, 0x3d3d3d3du); }
 
@@ -211,7 +221,7 @@ __device__ __forceinline__ uint4 eq16() { return make_uint4(0x3d3d3d3du, 0x3d3d3
 // by absolute position modulo RING, so a chunk is 128-byte aligned on both sides.  The capacity test lives here: a
 // read that comes within two chunks of its planned capacity is reported (the host re-plans the batch with more slack).
 __device__ __forceinline__ uint32_t flush_chunks(WarpSmem* ws, const ReadKernelParams& P, uint32_t ridx, uint32_t e_old, uint32_t e_new,
-                                                 uint32_t c_old, uint32_t c_new, uint32_t cap, int lane) {
+                                                 uint32_t c_old, uint32_t c_new, int lane) {
   __syncwarp();
   const uint64_t off = P.out_off[ridx];
   if (lane < 8) {
@@ -226,11 +236,11 @@ __device__ __forceinline__ uint32_t flush_chunks(WarpSmem* ws, const ReadKernelP
     }
   }
   __syncwarp();
-  return (max(e_new, c_new) + 2u * CHUNK > cap) ? (uint32_t)ST_OUT_OVERFLOW : (uint32_t)ST_OK;
+  return (max(e_new, c_new) + 2u * CHUNK > ws->st[ST_CAP]) ? (uint32_t)ST_OUT_OVERFLOW : (uint32_t)ST_OK;
 }
-__device__ __noinline__ uint32_t flush_chunks_cold(WarpSmem* ws, const ReadKernelParams& P, uint32_t ridx, uint32_t e_old, uint32_t e_new,
-                                                   uint32_t c_old, uint32_t c_new, uint32_t cap, int lane) {
-  return flush_chunks(ws, P, ridx, e_old, e_new, c_old, c_new, cap, lane);
+__device__ __noinline__ uint32_t flush_chunks_cold(uint32_t ws32, const ReadKernelParams& P, uint32_t ridx, uint32_t e_old, uint32_t e_new,
+                                                   uint32_t c_old, uint32_t c_new, int lane) {
+  return flush_chunks(smem_ptr(ws32), P, ridx, e_old, e_new, c_old, c_new, lane);
 }
 
 // Appends n positions to the stitch, at most 64 per step with a flush in between (cold path: long unchanged
@@ -238,7 +248,7 @@ __device__ __noinline__ uint32_t flush_chunks_cold(WarpSmem* ws, const ReadKerne
 // those ops go to the CIGAR; cig_eq: the CIGAR advances over its '=' pre-fill instead.
 __device__ __forceinline__ void stitch_append(Stitch& S, WarpSmem* ws, const ReadKernelParams& P, uint32_t ridx, const uint8_t* err_src,
                                               const uint8_t* cig_src, bool cig_eq, uint32_t n, int lane) {
-  for (uint32_t done = 0; done < n && S.status == ST_OK; done += 64) {
+  for (uint32_t done = 0; done < n && st_status(S) == ST_OK; done += 64) {
     const uint32_t m = min(64u, n - done);
     const uint32_t e_old = S.err_len, c_old = S.cig_len;
     for (uint32_t i = lane; i < m; i += 32) {
@@ -247,7 +257,7 @@ __device__ __forceinline__ void stitch_append(Stitch& S, WarpSmem* ws, const Rea
     }
     if (err_src) S.err_len += m;
     if (cig_src || cig_eq) S.cig_len += m;
-    if (((e_old ^ S.err_len) | (c_old ^ S.cig_len)) >= CHUNK) S.status = flush_chunks(ws, P, ridx, e_old, S.err_len, c_old, S.cig_len, S.cap, lane);
+    if (((e_old ^ S.err_len) | (c_old ^ S.cig_len)) >= CHUNK) st_fail(S, flush_chunks(ws, P, ridx, e_old, S.err_len, c_old, S.cig_len, lane));
     __syncwarp();
   }
 }
@@ -255,7 +265,7 @@ __device__ __forceinline__ void stitch_append(Stitch& S, WarpSmem* ws, const Rea
 // The bookkeeping half of AbsChanges::add_change (src/simulate/error.rs:173-193) with contain / overlap / merge /
 // update_align (error.rs:83-164): decides what happens to a change [ob, oe) carrying olen bytes and updates the state
 // of `changes.last()`.  What is left to the caller is to append the piece bytes [es, olen) after `gap` unchanged
-// bases, and to align them against raw[rs, re).
+// bases raw[gap_src ..), and to align them against raw[rs, re).
 struct ChangePlan {
   uint32_t es, rs, re, gap, gap_src;
   bool contained, fast;
@@ -265,17 +275,17 @@ struct ChangePlan {
 // the k-mer raw[ob..oe).  `fast` comes back true when the piece that gets aligned is a k-mer tail against the same tail:
 // a pushed change, or a merge into a last change whose raw and err ends coincide.  Then the CIGAR of the reference's LCS
 // alignment has a closed form (single edit) or was computed at load time (table), and no DP is run.
-__device__ __forceinline__ ChangePlan plan_change(Stitch& S, uint32_t ob, uint32_t oe, uint32_t olen, uint32_t fk) {
+__device__ __forceinline__ ChangePlan plan_change(Stitch& S, uint32_t L, uint32_t ob, uint32_t oe, uint32_t olen, uint32_t fk) {
   ChangePlan c;
   c.es = 0;
   c.gap = 0;
-  c.gap_src = S.pos_in_raw;
+  c.gap_src = 0;
   c.contained = false;
   c.fast = fk != 0;
   c.rs = c.re = 0;
   bool merge = false;
   if (S.flags & F_HAS_LAST) {
-    const uint32_t l_end_err = S.lb + S.lseq_len;
+    const uint32_t l_end_err = S.lee;
     if (oe <= l_end_err || oe <= S.le || ob + olen <= l_end_err) {  // contain (error.rs:83-88)
       c.contained = true;
       return c;
@@ -293,11 +303,11 @@ __device__ __forceinline__ ChangePlan plan_change(Stitch& S, uint32_t ob, uint32
         S.le = ob + olen;
         c.fast = false;
       }
-      if (S.le < S.L - 1) {
+      if (S.le < L - 1) {
         if (old_end < S.le) { c.rs = old_end; c.re = S.le; } else { c.rs = S.le; c.re = old_end; }
-      } else { c.rs = old_end; c.re = S.L; c.fast = false; }
-      if (c.rs > c.re || c.re > S.L || c.es > olen) { S.status = ST_REF_PANIC; c.contained = true; return c; }
-      S.lseq_len += olen - c.es;
+      } else { c.rs = old_end; c.re = L; c.fast = false; }
+      if (c.rs > c.re || c.re > L || c.es > olen) { st_fail(S, ST_REF_PANIC); c.contained = true; return c; }
+      S.lee += olen - c.es;
     }
   }
   if (!merge) {  // push a new change (update_align: error.rs:155-164)
@@ -306,12 +316,12 @@ __device__ __forceinline__ ChangePlan plan_change(Stitch& S, uint32_t ob, uint32
       S.pos_in_raw = S.le;
     }
     c.rs = ob;
-    c.re = oe > S.L ? S.L : oe;
-    if (c.rs > c.re) { S.status = ST_REF_PANIC; c.contained = true; return c; }
-    S.flags = F_HAS_LAST | (ob >= S.pos_in_raw ? F_EMIT : 0u);  // sequence(): `if change.begin() < pos_in_raw { continue }`
-    S.lb = ob;
+    c.re = oe > L ? L : oe;
+    if (c.rs > c.re) { st_fail(S, ST_REF_PANIC); c.contained = true; return c; }
+    // sequence(): `if change.begin() < pos_in_raw { continue }`
+    S.flags = (S.flags & ~(F_HAS_LAST | F_EMIT)) | F_HAS_LAST | (ob >= S.pos_in_raw ? F_EMIT : 0u);
     S.le = oe;
-    S.lseq_len = olen;
+    S.lee = ob + olen;
     S.ledit = 0;
     c.gap_src = S.pos_in_raw;
     c.gap = ob - S.pos_in_raw;  // only meaningful when F_EMIT
@@ -319,16 +329,31 @@ __device__ __forceinline__ ChangePlan plan_change(Stitch& S, uint32_t ob, uint32
   return c;
 }
 
+// The cold stages are out of line and exchange the stitch state through shared memory (WarpSmem::st): passing it by value
+// to a __noinline__ function makes the compiler keep it on the local-memory stack in the hot loop as well.
+__device__ __forceinline__ void st_save(WarpSmem* ws, const Stitch& S) {
+  __syncwarp();
+  ws->st[2] = S.err_len; ws->st[3] = S.cig_len; ws->st[4] = S.pos_in_raw; ws->st[5] = S.real_edit;
+  ws->st[6] = S.le; ws->st[7] = S.lee; ws->st[8] = S.ledit; ws->st[9] = S.flags;
+  __syncwarp();
+}
+__device__ __forceinline__ void st_load(const WarpSmem* ws, Stitch& S) {
+  __syncwarp();
+  S.err_len = ws->st[2]; S.cig_len = ws->st[3]; S.pos_in_raw = ws->st[4]; S.real_edit = ws->st[5];
+  S.le = ws->st[6]; S.lee = ws->st[7]; S.ledit = ws->st[8]; S.flags = ws->st[9];
+  __syncwarp();
+}
+
 // Cold form of add_change: the piece lives in memory (glitch inserts, table alternatives longer than a warp).
-struct ColdOut {
+// Stitch state in / out through ws->st; returns the edit count.
+__device__ __noinline__ uint32_t add_change_cold(uint32_t ws32, const ReadKernelParams& P, uint32_t ridx, const uint8_t* raw,
+                                                 uint32_t ob, uint32_t oe, const uint8_t* oseq, uint32_t olen, int lane) {
+  WarpSmem* ws = smem_ptr(ws32);
+  const uint32_t gwarp = blockIdx.x * WARPS_PER_BLOCK + (threadIdx.x >> 5);
   Stitch S;
-  uint32_t edits;
-};
-__device__ __noinline__ ColdOut add_change_cold(Stitch S, WarpSmem* ws, const ReadKernelParams& P, uint32_t gwarp, uint32_t ridx, const uint8_t* raw,
-                                                uint32_t ob, uint32_t oe, const uint8_t* oseq, uint32_t olen, int lane) {
-  ColdOut o;
-  o.edits = 0;
-  const ChangePlan c = plan_change(S, ob, oe, olen, 0);
+  st_load(ws, S);
+  uint32_t edits = 0;
+  const ChangePlan c = plan_change(S, ws->st[ST_L], ob, oe, olen, 0);
   if (!c.contained) {
     const uint32_t add = olen - c.es, tn = c.re - c.rs;
     const bool emit = (S.flags & F_EMIT) != 0;
@@ -340,42 +365,35 @@ __device__ __noinline__ ColdOut add_change_cold(Stitch S, WarpSmem* ws, const Re
     __syncwarp();
     const uint64_t a = warp_align(ws, P, gwarp, oseq + c.es, add, raw + c.rs, tn, emit ? fwd : nullptr, lane);
     __syncwarp();
-    if (align_status(a)) S.status = align_status(a);
+    if (align_status(a)) st_fail(S, align_status(a));
     else {
-      if (emit && S.status == ST_OK) stitch_append(S, ws, P, ridx, nullptr, fwd, false, align_nops(a), lane);
+      if (emit && st_status(S) == ST_OK) stitch_append(S, ws, P, ridx, nullptr, fwd, false, align_nops(a), lane);
       S.ledit += align_edits(a);
-      o.edits = align_edits(a);
+      edits = align_edits(a);
     }
   }
-  o.S = S;
-  return o;
+  st_save(ws, S);
+  return edits;
 }
 
 // Cold appends from the hot form of add_change: a long unchanged stretch raw[src, src + n) (err_src, the CIGAR advances
-// over its '=' pre-fill), or the ops of a large alignment (cig_src).  The lengths travel by value.
-struct AppendOut {
-  uint32_t err_len, cig_len, status;
-};
-__device__ __noinline__ AppendOut append_cold(WarpSmem* ws, const ReadKernelParams& P, uint32_t ridx, const uint8_t* err_src, const uint8_t* cig_src,
-                                              uint32_t n, uint32_t err_len, uint32_t cig_len, uint32_t cap, int lane) {
+// over its '=' pre-fill), or the ops of a large alignment (cig_src).  Lengths and status through ws->st.
+__device__ __noinline__ void append_cold(uint32_t ws32, const ReadKernelParams& P, uint32_t ridx, const uint8_t* err_src, const uint8_t* cig_src,
+                                         uint32_t n, int lane) {
+  WarpSmem* ws = smem_ptr(ws32);
   Stitch S;
-  S.err_len = err_len;
-  S.cig_len = cig_len;
-  S.cap = cap;
-  S.status = ST_OK;
+  st_load(ws, S);
   stitch_append(S, ws, P, ridx, err_src, cig_src, cig_src == nullptr, n, lane);
-  AppendOut g;
-  g.err_len = S.err_len;
-  g.cig_len = S.cig_len;
-  g.status = S.status;
-  return g;
+  st_save(ws, S);
 }
 
-// Alignment of a register-resident piece that the register aligner cannot take (window wider than a warp, or a byte
-// outside ACGT): the piece goes through shared memory to the general aligners.  Returns the packed alignment result;
-// the ops are left in forward order in the second half of the warp's op scratch.
-__device__ __noinline__ uint64_t align_piece_cold(WarpSmem* ws, const ReadKernelParams& P, uint32_t gwarp, uint32_t c, uint32_t es, uint32_t olen,
+// Alignment of a register-resident piece that the register aligner cannot take (window wider than a warp, more than
+// 16 ops, or a byte outside ACGT): the piece goes through shared memory to the general aligners.  Returns the packed
+// alignment result; the ops are left in forward order in the second half of the warp's op scratch.
+__device__ __noinline__ uint64_t align_piece_cold(uint32_t ws32, const ReadKernelParams& P, uint32_t c, uint32_t es, uint32_t olen,
                                                   const uint8_t* t, uint32_t tn, bool emit, int lane) {
+  WarpSmem* ws = smem_ptr(ws32);
+  const uint32_t gwarp = blockIdx.x * WARPS_PER_BLOCK + (threadIdx.x >> 5);
   __syncwarp();
   if ((uint32_t)lane < olen) ws->alt[lane] = (uint8_t)c;  // olen <= 32
   __syncwarp();
@@ -393,10 +411,10 @@ __device__ __noinline__ uint64_t align_piece_cold(WarpSmem* ws, const ReadKernel
 // tie-break), the edit then slides left while the neighbouring bases are equal (still matches), and where it stops the
 // two prefixes are identical, which forces X / I / D there and '=' before it.  Checked against the DP + tie-break
 // exhaustively for all k-mers up to k = 7 over 1-, 2- and 4-letter alphabets and for every piece offset.
-__device__ __forceinline__ uint32_t add_change_reg(Stitch& S, WarpSmem* ws, const ReadKernelParams& P, uint32_t gwarp, uint32_t ridx, const uint8_t* raw,
+__device__ __forceinline__ uint32_t add_change_reg(Stitch& S, WarpSmem* ws, const ReadKernelParams& P, uint32_t L, uint32_t ridx, const uint8_t* raw,
                                                    uint32_t ob, uint32_t oe, uint32_t c, uint32_t olen, uint32_t fk, uint32_t fep, uint32_t kb,
                                                    int lane) {
-  const ChangePlan cp = plan_change(S, ob, oe, olen, fk);
+  const ChangePlan cp = plan_change(S, L, ob, oe, olen, fk);
   if (cp.contained) return 0;
   const uint32_t es = cp.es, add = olen - es, tn = cp.re - cp.rs;
   const bool emit = (S.flags & F_EMIT) != 0;
@@ -408,10 +426,12 @@ __device__ __forceinline__ uint32_t add_change_reg(Stitch& S, WarpSmem* ws, cons
         S.err_len += cp.gap;
         S.cig_len += cp.gap;  // the CIGAR ring is pre-filled with '='
       } else {
-        const AppendOut g = append_cold(ws, P, ridx, raw + cp.gap_src, nullptr, cp.gap, S.err_len, S.cig_len, S.cap, lane);
-        e_old = S.err_len = g.err_len;  // append_cold has flushed its own chunks
-        c_old = S.cig_len = g.cig_len;
-        if (g.status) { S.status = g.status; return 0; }
+        st_save(ws, S);
+        append_cold(smem_addr(ws), P, ridx, raw + cp.gap_src, nullptr, cp.gap, lane);
+        st_load(ws, S);
+        e_old = S.err_len;  // append_cold has flushed its own chunks
+        c_old = S.cig_len;
+        if (st_status(S)) return 0;
       }
     }
     if ((uint32_t)lane >= es && (uint32_t)lane < olen) ws->errb[(S.err_len + lane - es) & (RING - 1u)] = (uint8_t)c;
@@ -445,21 +465,22 @@ __device__ __forceinline__ uint32_t add_change_reg(Stitch& S, WarpSmem* ws, cons
     if (emit && (uint32_t)lane < nops) ws->cigb[(S.cig_len + lane) & (RING - 1u)] = add == 0 ? 'D' : 'I';
   } else {
     uint64_t a = ~0ULL;
-    if (tn <= 32u && add <= 31u && add != 0 && tn != 0) {
+    if (add + tn <= 16u && add != 0 && tn != 0) {
       const uint32_t qc = __shfl_sync(0xffffffffu, c, (lane - 1 + (int)es) & 31);
       const uint32_t tc = (uint32_t)lane < tn ? raw[cp.rs + lane] : (uint32_t)'A';
-      a = warp_align_regs<true>(qc, add, tc, tn, emit ? ws->cigb : nullptr, S.cig_len, lane);
+      a = warp_align_small(qc, add, tc, tn, emit ? ws->cigb : nullptr, S.cig_len, lane);
     }
-    if (a == ~0ULL) {  // window wider than a warp or a byte outside ACGT: general aligners, ops through the scratch
-      a = align_piece_cold(ws, P, gwarp, c, es, olen, raw + cp.rs, tn, emit, lane);
-      if (align_status(a)) { S.status = align_status(a); return 0; }
+    if (a == ~0ULL) {  // more than 16 ops or a byte outside ACGT: general aligners, ops through the scratch
+      a = align_piece_cold(smem_addr(ws), P, c, es, olen, raw + cp.rs, tn, emit, lane);
+      if (align_status(a)) { st_fail(S, align_status(a)); return 0; }
       if (emit) {
         // flush what this event staged so far, then append the ops (possibly more than a ring's worth)
-        if (((e_old ^ S.err_len) | (c_old ^ S.cig_len)) >= CHUNK) S.status = flush_chunks_cold(ws, P, ridx, e_old, S.err_len, c_old, S.cig_len, S.cap, lane);
+        if (((e_old ^ S.err_len) | (c_old ^ S.cig_len)) >= CHUNK) st_fail(S, flush_chunks_cold(smem_addr(ws), P, ridx, e_old, S.err_len, c_old, S.cig_len, lane));
+        const uint32_t gwarp = blockIdx.x * WARPS_PER_BLOCK + (threadIdx.x >> 5);
         const uint8_t* fwd = P.sc_ops + (uint64_t)gwarp * P.sc_ops_cap + P.sc_ops_cap / 2;
-        const AppendOut g = append_cold(ws, P, ridx, nullptr, fwd, align_nops(a), S.err_len, S.cig_len, S.cap, lane);
-        S.cig_len = g.cig_len;
-        if (g.status) S.status = g.status;
+        st_save(ws, S);
+        append_cold(smem_addr(ws), P, ridx, nullptr, fwd, align_nops(a), lane);
+        st_load(ws, S);
       }
       S.ledit += align_edits(a);
       return align_edits(a);
@@ -469,63 +490,61 @@ __device__ __forceinline__ uint32_t add_change_reg(Stitch& S, WarpSmem* ws, cons
   }
   if (emit) {
     S.cig_len += nops;
-    if (((e_old ^ S.err_len) | (c_old ^ S.cig_len)) >= CHUNK) {
-      const uint32_t st = flush_chunks_cold(ws, P, ridx, e_old, S.err_len, c_old, S.cig_len, S.cap, lane);
-      if (st) S.status = st;
-    }
+    if (((e_old ^ S.err_len) | (c_old ^ S.cig_len)) >= CHUNK) st_fail(S, flush_chunks_cold(smem_addr(ws), P, ridx, e_old, S.err_len, c_old, S.cig_len, lane));
   }
   S.ledit += ed;
   return ed;
 }
 
-__device__ __forceinline__ void process_read(const ReadKernelParams& P, WarpSmem* ws, uint32_t gwarp, uint32_t ridx, int lane) {
+__device__ __forceinline__ void process_read(const ReadKernelParams& P, WarpSmem* ws, uint32_t ridx, int lane) {
   const DeviceModels& M = P.M;
   const uint32_t k = M.k;
+  const uint32_t ws32 = smem_addr(ws);
   WarpRng rng;
-  rng.seed(P.descs[ridx].seed, ws->rng, lane);
+  rng.seed(P.descs[ridx].seed, ws, lane);
 
   uint8_t* raw = P.raw + P.raw_off[ridx];
-  StageOut so = stage_assemble(rng, P, ws, ridx, raw);
-  rng.set_cursor(so.base, so.cur);
+  StageOut so = stage_assemble(ws32, rng.off, lane, P, ridx, raw);
+  rng.off = so.off;
   const uint32_t L = (uint32_t)so.value;
 
   Stitch S;
-  S.L = L;
-  S.cap = (uint32_t)(P.out_off[ridx + 1] - P.out_off[ridx]);
   S.err_len = S.cig_len = 0;
   S.pos_in_raw = 0;
   S.real_edit = 0;
   S.flags = 0;
-  S.lb = S.le = S.lseq_len = S.ledit = 0;
-  S.status = ST_OK;
+  S.le = S.lee = S.ledit = 0;
+  __syncwarp();
+  ws->st[ST_L] = L;
+  ws->st[ST_CAP] = (uint32_t)(P.out_off[ridx + 1] - P.out_off[ridx]);
   if (lane < (int)(RING / 16)) *reinterpret_cast<uint4*>(&ws->cigb[16 * lane]) = eq16();
   __syncwarp();
 
   // ---- K3: error::sequence (src/simulate/error.rs:201-217) ----
   double target = (1.0 - P.descs[ridx].identity) * (double)L;  // number_of_edit, error.rs:196-198
-  uint32_t ng = 0;
+  uint32_t gbegin = ~0u;  // raw position of the next glitch
   if (M.has_distance) {
-    so = stage_glitches(rng, P, gwarp, L);
-    rng.set_cursor(so.base, so.cur);
-    ng = (uint32_t)so.value;
-    S.status = so.status;
+    const uint32_t gwarp = blockIdx.x * WARPS_PER_BLOCK + (threadIdx.x >> 5);
+    so = stage_glitches(ws32, rng.off, lane, P, gwarp, L);
+    rng.off = so.off;
+    st_fail(S, so.status);
+    __syncwarp();
+    ws->st[ST_G] = 0;
+    ws->st[ST_NG] = (uint32_t)so.value;
+    if (so.value) gbegin = (uint32_t)P.sc_grec[(uint64_t)gwarp * P.sc_grec_cap].begin;
   }
 
   // add_error (error.rs:267-302): one Bernoulli(target / (L - pos)) per position.  32 positions are
   // tried at once against the current target; the first lane with an event wins.
-  if (S.status == ST_OK) {
-    const uint32_t nlim = L - k;
+  if (st_status(S) == ST_OK) {
     uint32_t pos = 0;
-    uint32_t g = 0;
-    uint32_t gbegin = ng ? (uint32_t)P.sc_grec[(uint64_t)gwarp * P.sc_grec_cap].begin : ~0u;
-    bool glitch_checked = false;
-    while (pos < nlim) {
+    while (pos < L - k) {
       rng.need(64 + 32);  // 64 words for the 32 positions + spare for the draws of the event (WarpRng hot draws)
       const uint32_t pi = pos + (uint32_t)lane;
-      const bool inb = pi < nlim;
+      const bool inb = pi < L - k;
       const double rem = (double)(L - pi);
       const bool brk = target < 0.0 || target > rem;
-      const bool gl = (pi == gbegin) && !(lane == 0 && glitch_checked);
+      const bool gl = (pi == gbegin) && !(lane == 0 && (S.flags & F_GLITCH_CHECKED));
       const double p = target / rem;
       const bool one = (p == 1.0);
       const uint64_t v = rng.peek64_at(rng.off + 2 * (uint32_t)lane);
@@ -534,7 +553,7 @@ __device__ __forceinline__ void process_read(const ReadKernelParams& P, WarpSmem
       if (m_any == 0) {
         pos += 32;
         rng.off += 64;
-        glitch_checked = false;
+        S.flags &= ~F_GLITCH_CHECKED;
         continue;
       }
       const int f = __ffs(m_any) - 1;
@@ -543,20 +562,23 @@ __device__ __forceinline__ void process_read(const ReadKernelParams& P, WarpSmem
       if (f > 0) {
         pos += (uint32_t)f;
         rng.off += 2 * (uint32_t)f;
-        glitch_checked = false;
+        S.flags &= ~F_GLITCH_CHECKED;
       }
       if (!(ff & 1u)) break;  // pos == L - k
       uint32_t edits;
       const bool is_glitch = (ff & 2u) != 0;
       if (is_glitch) {  // glitch due at pos (error.rs:282-287)
+        const uint32_t gwarp = blockIdx.x * WARPS_PER_BLOCK + (threadIdx.x >> 5);
         const GlitchRec* grec = P.sc_grec + (uint64_t)gwarp * P.sc_grec_cap;
+        const uint32_t g = ws->st[ST_G];
         const GlitchRec gr = grec[g];
-        ++g;
-        gbegin = (g < ng) ? (uint32_t)grec[g].begin : ~0u;
-        const ColdOut co = add_change_cold(S, ws, P, gwarp, ridx, raw, (uint32_t)gr.begin, (uint32_t)gr.end,
-                                           P.sc_gseq + (uint64_t)gwarp * P.sc_gseq_cap + gr.seq_off, gr.seq_len, lane);
-        S = co.S;
-        edits = co.edits;
+        gbegin = (g + 1 < ws->st[ST_NG]) ? (uint32_t)grec[g + 1].begin : ~0u;
+        st_save(ws, S);
+        ws->st[ST_G] = g + 1;
+        edits = add_change_cold(ws32, P, ridx, raw, (uint32_t)gr.begin, (uint32_t)gr.end,
+                                P.sc_gseq + (uint64_t)gwarp * P.sc_gseq_cap + gr.seq_off, gr.seq_len, lane);
+        st_load(ws, S);
+        S.flags |= F_GLITCH_CHECKED;  // same pos again, with the new target, glitch check done
       } else {
         if (ff & 4u) break;  // error.rs:289-291
         if (!(ff & 8u)) rng.off += 2;
@@ -575,23 +597,19 @@ __device__ __forceinline__ void process_read(const ReadKernelParams& P, WarpSmem
           if (!__any_sync(0xffffffffu, bad)) key = M.em_index[code];
         }
         if (key >= 0) {
-          so = stage_alt_from_table(rng, M, key);
-          rng.set_cursor(so.base, so.cur);
+          so = stage_alt_from_table(ws32, rng.off, lane, M, key);
+          rng.off = so.off;
           olen = (uint32_t)so.value;
           fk = 4;
           fep = so.status;
           const uint32_t o0 = M.em_alt_off[fep];
           if (olen <= 32u) {
             if ((uint32_t)lane < olen) c = M.em_alt_bytes[o0 + lane];
+            edits = add_change_reg(S, ws, P, L, ridx, raw, pos, pos + k, c, olen, fk, fep, kb, lane);
           } else {  // an alternative longer than a warp: through memory
-            const ColdOut co = add_change_cold(S, ws, P, gwarp, ridx, raw, pos, pos + k, M.em_alt_bytes + o0, olen, lane);
-            S = co.S;
-            target -= (double)co.edits;
-            if (S.status) break;
-            if (target < 0.0 || target > (double)(L - pos)) break;  // error.rs:298-300
-            pos += 1;
-            glitch_checked = false;
-            continue;
+            st_save(ws, S);
+            edits = add_change_cold(ws32, P, ridx, raw, pos, pos + k, M.em_alt_bytes + o0, olen, lane);
+            st_load(ws, S);
           }
         } else {  // random_error (src/model/error.rs:116-135)
           const uint32_t ep = rng.gen_index_hot(k);
@@ -612,61 +630,55 @@ __device__ __forceinline__ void process_read(const ReadKernelParams& P, WarpSmem
           }
           fk = kind;
           fep = ep;
+          edits = add_change_reg(S, ws, P, L, ridx, raw, pos, pos + k, c, olen, fk, fep, kb, lane);
         }
-        edits = add_change_reg(S, ws, P, gwarp, ridx, raw, pos, pos + k, c, olen, fk, fep, kb, lane);
       }
       target -= (double)edits;
-      if (S.status) break;
-      if (is_glitch) {
-        glitch_checked = true;  // same pos again, with the new target, glitch check done
-      } else {
+      if (st_status(S)) break;
+      if (!is_glitch) {
         if (target < 0.0 || target > (double)(L - pos)) break;  // error.rs:298-300
         pos += 1;
-        glitch_checked = false;
+        S.flags &= ~F_GLITCH_CHECKED;
       }
     }
   }
 
   // ---- K5: tail of the stitch (error.rs:241-246) ----
-  if (S.status == ST_OK) {
+  if (st_status(S) == ST_OK) {
     if ((S.flags & (F_HAS_LAST | F_EMIT)) == (F_HAS_LAST | F_EMIT)) {
       S.real_edit += S.ledit;
       S.pos_in_raw = S.le;
     }
     if (S.pos_in_raw < L) {
-      const AppendOut gpo = append_cold(ws, P, ridx, raw + S.pos_in_raw, nullptr, L - S.pos_in_raw, S.err_len, S.cig_len, S.cap, lane);
-      S.err_len = gpo.err_len;
-      S.cig_len = gpo.cig_len;
-      S.status = gpo.status;
+      st_save(ws, S);
+      append_cold(ws32, P, ridx, raw + S.pos_in_raw, nullptr, L - S.pos_in_raw, lane);
+      st_load(ws, S);
     }
     // the partial last chunks (the chunk past max(len) stays inside the capacity: see flush_chunks)
-    const uint32_t st = flush_chunks_cold(ws, P, ridx, S.err_len, S.err_len + CHUNK, S.cig_len, S.cig_len + CHUNK, ~0u, lane);
-    (void)st;
+    (void)flush_chunks_cold(ws32, P, ridx, S.err_len, S.err_len + CHUNK, S.cig_len, S.cig_len + CHUNK, lane);
   }
   __syncwarp();
   if (lane == 0) {
+    const uint32_t status = st_status(S);
     P.raw_len[ridx] = L;
-    P.err_len[ridx] = S.status ? 0 : S.err_len;
-    P.cig_len[ridx] = S.status ? 0 : S.cig_len;
+    P.err_len[ridx] = status ? 0 : S.err_len;
+    P.cig_len[ridx] = status ? 0 : S.cig_len;
     P.q_cursor[ridx] = rng.cursor();
     P.real_id[ridx] = (1.0 - ((double)S.real_edit / (double)L)) * 100.0;  // error.rs:246, mod.rs:289
-    P.status[ridx] = S.status;
+    P.status[ridx] = status;
   }
 }
 
 __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, RR_BLOCKS_PER_SM) rr_read_kernel(const __grid_constant__ ReadKernelParams P) {
   __shared__ WarpSmem smem[WARPS_PER_BLOCK];
-  const int warp = threadIdx.x >> 5;
-  int lane;
-  asm volatile("mov.u32 %0, %%laneid;" : "=r"(lane));  // volatile: kept in a register instead of being re-read from SR_TID at every use
-  const uint32_t gwarp = blockIdx.x * WARPS_PER_BLOCK + warp;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   WarpSmem* ws = &smem[warp];
   for (;;) {
     uint32_t slot = 0;
     if (lane == 0) slot = atomicAdd(P.queue, 1u);
     slot = __shfl_sync(0xffffffffu, slot, 0);
     if (slot >= P.n_reads) break;
-    process_read(P, ws, gwarp, P.order[slot], lane);
+    process_read(P, ws, P.order[slot], lane);
     __syncwarp();
   }
 }
