@@ -172,43 +172,57 @@ __device__ __noinline__ StageOut stage_glitches(uint32_t ws32, uint32_t off, int
   return o;
 }
 
-// Error::add_errors_to_kmer on a k-mer that is in the table (src/model/error.rs:96-100): one WeightedIndex draw.
-// Out of line: only file models reach it.  value = alternative length, status = global id of the chosen alternative
-// (it indexes em_alt_off and the precomputed alignments).
-__device__ __noinline__ StageOut stage_alt_from_table(uint32_t ws32, uint32_t off, int lane, const DeviceModels& M, int key) {
-  WarpRng rng = stage_rng(ws32, off, lane);
-  uint32_t a0 = M.em_alt_begin[key], a1 = M.em_alt_begin[key + 1];
-  uint32_t na = a1 - a0;
-  double chosen = u64_to_unit12(rng.next_u64()) * M.em_scale[key] + 0.0;
-  uint32_t idx = 0;  // number of partial sums <= chosen among the first na - 1
-  for (uint32_t b = 0; b + 1 < na; b += 32) {
-    uint32_t i = b + lane;
-    bool le = (i + 1 < na) && (M.em_cum[a0 + i] <= chosen);
-    idx += __popc(__ballot_sync(0xffffffffu, le));
-  }
-  StageOut o;
-  o.off = rng.off;
-  o.value = M.em_alt_off[a0 + idx + 1] - M.em_alt_off[a0 + idx];
-  o.status = a0 + idx;
-  return o;
-}
-
 // State of `changes.last()` plus the streamed stitch of sequence() (src/simulate/error.rs:219-246).
 // A Change only ever grows by appending to seq / cigar (merge, error.rs:105-152), and only the last
 // one can change, so err / CIGAR are written once, in order, as the walk proceeds: into the warp's staging rings
 // (WarpSmem::errb / cigb), from which complete 128-byte chunks leave for HBM.
 // All positions are 32-bit: the host refuses reads whose raw capacity reaches 2^30 bases.
-// The hot loop keeps this in registers, so it is kept small: the last change is (le = its end in raw, lee = its end in
-// err coordinates = begin + seq.len(), ledit); L, the capacity and the glitch cursor live in WarpSmem::st.
+// The last change is (le = its end in raw, lee = its end in err coordinates = begin + seq.len(), ledit).
 struct Stitch {
   uint32_t err_len, cig_len;
   uint32_t pos_in_raw;   // sequence(): end of the last emitted change
   uint32_t real_edit;
   uint32_t le, lee, ledit;
-  uint32_t flags;        // F_HAS_LAST | F_EMIT | F_GLITCH_CHECKED | status << 8
+  uint32_t flags;        // F_HAS_LAST | F_EMIT | F_GLITCH_CHECKED | F_REPLAY | F_REPLAYED | status << 8
 };
-enum : uint32_t { F_HAS_LAST = 1u, F_EMIT = 2u, F_GLITCH_CHECKED = 4u, F_STATUS_SHIFT = 8u };
-enum : int { ST_L = 0, ST_CAP = 1, ST_G = 12, ST_NG = 13 };  // WarpSmem::st slots that are not Stitch fields
+enum : uint32_t { F_HAS_LAST = 1u, F_EMIT = 2u, F_GLITCH_CHECKED = 4u, F_REPLAY = 8u, F_REPLAYED = 16u, F_STATUS_SHIFT = 8u };
+
+// Everything the error walk carries from one position to the next.  The walk keeps it in registers; around EVERY
+// out-of-line call inside the loop it is parked in WarpSmem::st and read back, so that no value is live across a call:
+// the calling convention would otherwise push the whole state to the local-memory stack, and ptxas then reloads it at
+// every use in the hot path (first ncu captures of this kernel: 35 LDL/STL per event).
+struct Walk {
+  uint32_t pos, off;       // position in raw; next word of the read's stream (relative to WarpSmem::rng_base)
+  uint32_t L, gbegin;      // raw length; raw position of the next glitch (~0: none)
+  uint32_t ridx;
+  double target;
+  const uint8_t* raw;
+  Stitch S;
+};
+enum : int { ST_L = 0, ST_CAP = 1, ST_ERR_LEN = 2, ST_CIG_LEN = 3, ST_POS_IN_RAW = 4, ST_REAL_EDIT = 5, ST_LE = 6, ST_LEE = 7, ST_LEDIT = 8,
+             ST_FLAGS = 9, ST_POS = 10, ST_OFF = 11, ST_G = 12, ST_NG = 13, ST_TARGET = 14 /* 2 words */, ST_GBEGIN = 16, ST_RIDX = 17,
+             ST_RAW = 18 /* 2 words */ };
+
+__device__ __forceinline__ void walk_save(WarpSmem* ws, const Walk& W) {  // every lane writes the same values
+  __syncwarp();
+  uint32_t* st = ws->st;
+  st[ST_L] = W.L; st[ST_ERR_LEN] = W.S.err_len; st[ST_CIG_LEN] = W.S.cig_len; st[ST_POS_IN_RAW] = W.S.pos_in_raw; st[ST_REAL_EDIT] = W.S.real_edit;
+  st[ST_LE] = W.S.le; st[ST_LEE] = W.S.lee; st[ST_LEDIT] = W.S.ledit; st[ST_FLAGS] = W.S.flags; st[ST_POS] = W.pos; st[ST_OFF] = W.off;
+  st[ST_GBEGIN] = W.gbegin; st[ST_RIDX] = W.ridx;
+  *reinterpret_cast<double*>(&st[ST_TARGET]) = W.target;
+  *reinterpret_cast<const uint8_t**>(&st[ST_RAW]) = W.raw;
+  __syncwarp();
+}
+__device__ __forceinline__ void walk_load(const WarpSmem* ws, Walk& W) {
+  __syncwarp();
+  const uint32_t* st = ws->st;
+  W.L = st[ST_L]; W.S.err_len = st[ST_ERR_LEN]; W.S.cig_len = st[ST_CIG_LEN]; W.S.pos_in_raw = st[ST_POS_IN_RAW]; W.S.real_edit = st[ST_REAL_EDIT];
+  W.S.le = st[ST_LE]; W.S.lee = st[ST_LEE]; W.S.ledit = st[ST_LEDIT]; W.S.flags = st[ST_FLAGS]; W.pos = st[ST_POS]; W.off = st[ST_OFF];
+  W.gbegin = st[ST_GBEGIN]; W.ridx = st[ST_RIDX];
+  W.target = *reinterpret_cast<const double*>(&st[ST_TARGET]);
+  W.raw = *reinterpret_cast<const uint8_t* const*>(&st[ST_RAW]);
+  __syncwarp();
+}
 
 __device__ __forceinline__ uint32_t st_status(const Stitch& S) { return S.flags >> F_STATUS_SHIFT; }
 __device__ __forceinline__ void st_fail(Stitch& S, uint32_t status) {
@@ -238,13 +252,9 @@ __device__ __forceinline__ uint32_t flush_chunks(WarpSmem* ws, const ReadKernelP
   __syncwarp();
   return (max(e_new, c_new) + 2u * CHUNK > ws->st[ST_CAP]) ? (uint32_t)ST_OUT_OVERFLOW : (uint32_t)ST_OK;
 }
-__device__ __noinline__ uint32_t flush_chunks_cold(uint32_t ws32, const ReadKernelParams& P, uint32_t ridx, uint32_t e_old, uint32_t e_new,
-                                                   uint32_t c_old, uint32_t c_new, int lane) {
-  return flush_chunks(smem_ptr(ws32), P, ridx, e_old, e_new, c_old, c_new, lane);
-}
 
-// Appends n positions to the stitch, at most 64 per step with a flush in between (cold path: long unchanged
-// stretches, glitch inserts, large alignments).  err_src != nullptr: those bytes go to the sequence; cig_src != nullptr:
+// Appends n positions to the stitch, at most 64 per step with a flush in between (cold path: glitch inserts, large
+// alignments, the tail of the read).  err_src != nullptr: those bytes go to the sequence; cig_src != nullptr:
 // those ops go to the CIGAR; cig_eq: the CIGAR advances over its '=' pre-fill instead.
 __device__ __forceinline__ void stitch_append(Stitch& S, WarpSmem* ws, const ReadKernelParams& P, uint32_t ridx, const uint8_t* err_src,
                                               const uint8_t* cig_src, bool cig_eq, uint32_t n, int lane) {
@@ -329,78 +339,91 @@ __device__ __forceinline__ ChangePlan plan_change(Stitch& S, uint32_t L, uint32_
   return c;
 }
 
-// The cold stages are out of line and exchange the stitch state through shared memory (WarpSmem::st): passing it by value
-// to a __noinline__ function makes the compiler keep it on the local-memory stack in the hot loop as well.
-__device__ __forceinline__ void st_save(WarpSmem* ws, const Stitch& S) {
+// ---- out-of-line stages of the walk: walk state in / out through WarpSmem::st ----
+
+// refill of the resident stream words (every ~25 events)
+__device__ __noinline__ void walk_refill(uint32_t ws32, int lane) {
+  WarpSmem* ws = smem_ptr(ws32);
+  const uint32_t off = rng_refill(ws32, ws->st[ST_OFF], lane);
   __syncwarp();
-  ws->st[2] = S.err_len; ws->st[3] = S.cig_len; ws->st[4] = S.pos_in_raw; ws->st[5] = S.real_edit;
-  ws->st[6] = S.le; ws->st[7] = S.lee; ws->st[8] = S.ledit; ws->st[9] = S.flags;
-  __syncwarp();
-}
-__device__ __forceinline__ void st_load(const WarpSmem* ws, Stitch& S) {
-  __syncwarp();
-  S.err_len = ws->st[2]; S.cig_len = ws->st[3]; S.pos_in_raw = ws->st[4]; S.real_edit = ws->st[5];
-  S.le = ws->st[6]; S.lee = ws->st[7]; S.ledit = ws->st[8]; S.flags = ws->st[9];
+  ws->st[ST_OFF] = off;
   __syncwarp();
 }
 
 // Cold form of add_change: the piece lives in memory (glitch inserts, table alternatives longer than a warp).
-// Stitch state in / out through ws->st; returns the edit count.
-__device__ __noinline__ uint32_t add_change_cold(uint32_t ws32, const ReadKernelParams& P, uint32_t ridx, const uint8_t* raw,
-                                                 uint32_t ob, uint32_t oe, const uint8_t* oseq, uint32_t olen, int lane) {
+// Returns the edit count.
+__device__ __noinline__ uint32_t add_change_cold(uint32_t ws32, int lane, const ReadKernelParams& P, uint32_t ob, uint32_t oe, const uint8_t* oseq,
+                                                 uint32_t olen) {
   WarpSmem* ws = smem_ptr(ws32);
   const uint32_t gwarp = blockIdx.x * WARPS_PER_BLOCK + (threadIdx.x >> 5);
-  Stitch S;
-  st_load(ws, S);
+  Walk W;
+  walk_load(ws, W);
+  Stitch& S = W.S;
   uint32_t edits = 0;
-  const ChangePlan c = plan_change(S, ws->st[ST_L], ob, oe, olen, 0);
+  const ChangePlan c = plan_change(S, W.L, ob, oe, olen, 0);
   if (!c.contained) {
     const uint32_t add = olen - c.es, tn = c.re - c.rs;
     const bool emit = (S.flags & F_EMIT) != 0;
     uint8_t* fwd = P.sc_ops + (uint64_t)gwarp * P.sc_ops_cap + P.sc_ops_cap / 2;  // ops in forward order (second half of the scratch)
     if (emit) {
-      if (c.gap) stitch_append(S, ws, P, ridx, raw + c.gap_src, nullptr, true, c.gap, lane);
-      stitch_append(S, ws, P, ridx, oseq + c.es, nullptr, false, add, lane);
+      if (c.gap) stitch_append(S, ws, P, W.ridx, W.raw + c.gap_src, nullptr, true, c.gap, lane);
+      stitch_append(S, ws, P, W.ridx, oseq + c.es, nullptr, false, add, lane);
     }
     __syncwarp();
-    const uint64_t a = warp_align(ws, P, gwarp, oseq + c.es, add, raw + c.rs, tn, emit ? fwd : nullptr, lane);
+    const uint64_t a = warp_align(ws, P, gwarp, oseq + c.es, add, W.raw + c.rs, tn, emit ? fwd : nullptr, lane);
     __syncwarp();
     if (align_status(a)) st_fail(S, align_status(a));
     else {
-      if (emit && st_status(S) == ST_OK) stitch_append(S, ws, P, ridx, nullptr, fwd, false, align_nops(a), lane);
+      if (emit && st_status(S) == ST_OK) stitch_append(S, ws, P, W.ridx, nullptr, fwd, false, align_nops(a), lane);
       S.ledit += align_edits(a);
       edits = align_edits(a);
     }
   }
-  st_save(ws, S);
+  walk_save(ws, W);
   return edits;
 }
 
-// Cold appends from the hot form of add_change: a long unchanged stretch raw[src, src + n) (err_src, the CIGAR advances
-// over its '=' pre-fill), or the ops of a large alignment (cig_src).  Lengths and status through ws->st.
-__device__ __noinline__ void append_cold(uint32_t ws32, const ReadKernelParams& P, uint32_t ridx, const uint8_t* err_src, const uint8_t* cig_src,
-                                         uint32_t n, int lane) {
+// The unchanged tail raw[pos_in_raw, L) of the read, then the partial last chunks of both rings.
+__device__ __noinline__ void walk_finish(uint32_t ws32, int lane, const ReadKernelParams& P) {
   WarpSmem* ws = smem_ptr(ws32);
-  Stitch S;
-  st_load(ws, S);
-  stitch_append(S, ws, P, ridx, err_src, cig_src, cig_src == nullptr, n, lane);
-  st_save(ws, S);
+  Walk W;
+  walk_load(ws, W);
+  Stitch& S = W.S;
+  if (S.pos_in_raw < W.L) stitch_append(S, ws, P, W.ridx, W.raw + S.pos_in_raw, nullptr, true, W.L - S.pos_in_raw, lane);
+  // the chunk past max(len) stays inside the capacity: see flush_chunks
+  if (st_status(S) == ST_OK) (void)flush_chunks(ws, P, W.ridx, S.err_len, S.err_len + CHUNK, S.cig_len, S.cig_len + CHUNK, lane);
+  walk_save(ws, W);
 }
 
-// Alignment of a register-resident piece that the register aligner cannot take (window wider than a warp, more than
-// 16 ops, or a byte outside ACGT): the piece goes through shared memory to the general aligners.  Returns the packed
-// alignment result; the ops are left in forward order in the second half of the warp's op scratch.
-__device__ __noinline__ uint64_t align_piece_cold(uint32_t ws32, const ReadKernelParams& P, uint32_t c, uint32_t es, uint32_t olen,
-                                                  const uint8_t* t, uint32_t tn, bool emit, int lane) {
+// Alignment of a register-resident piece that the register aligner cannot take (more than 16 ops, or a byte outside
+// ACGT): the piece goes through shared memory to the general aligners and its ops are appended to the CIGAR.
+// The event's err bytes are already staged: the chunks they completed are flushed here as well (e_old, c_old = the ring
+// positions at the start of the event).  Returns the edit count; lengths / status through the walk state.
+__device__ __noinline__ uint32_t align_piece_cold(uint32_t ws32, int lane, const ReadKernelParams& P, uint32_t c, uint32_t es, uint32_t olen,
+                                                  uint32_t rs, uint32_t tn, uint32_t e_old, uint32_t c_old) {
   WarpSmem* ws = smem_ptr(ws32);
   const uint32_t gwarp = blockIdx.x * WARPS_PER_BLOCK + (threadIdx.x >> 5);
-  __syncwarp();
+  Walk W;
+  walk_load(ws, W);
+  Stitch& S = W.S;
+  const bool emit = (S.flags & F_EMIT) != 0;
   if ((uint32_t)lane < olen) ws->alt[lane] = (uint8_t)c;  // olen <= 32
   __syncwarp();
   uint8_t* fwd = P.sc_ops + (uint64_t)gwarp * P.sc_ops_cap + P.sc_ops_cap / 2;
-  const uint64_t a = warp_align(ws, P, gwarp, ws->alt + es, olen - es, t, tn, emit ? fwd : nullptr, lane);
+  const uint64_t a = warp_align(ws, P, gwarp, ws->alt + es, olen - es, W.raw + rs, tn, emit ? fwd : nullptr, lane);
   __syncwarp();
-  return a;
+  uint32_t edits = 0;
+  if (align_status(a)) st_fail(S, align_status(a));
+  else {
+    if (emit) {
+      if (((e_old ^ S.err_len) | (c_old ^ S.cig_len)) >= CHUNK) st_fail(S, flush_chunks(ws, P, W.ridx, e_old, S.err_len, c_old, S.cig_len, lane));
+      stitch_append(S, ws, P, W.ridx, nullptr, fwd, false, align_nops(a), lane);
+    }
+    edits = align_edits(a);
+    S.ledit += edits;
+  }
+  walk_save(ws, W);
+  return edits;
 }
 
 // Hot form of add_change: the piece (olen <= 32 bytes) lives in registers, lane i holding byte i in `c`; `kb` holds the
@@ -411,86 +434,82 @@ __device__ __noinline__ uint64_t align_piece_cold(uint32_t ws32, const ReadKerne
 // tie-break), the edit then slides left while the neighbouring bases are equal (still matches), and where it stops the
 // two prefixes are identical, which forces X / I / D there and '=' before it.  Checked against the DP + tie-break
 // exhaustively for all k-mers up to k = 7 over 1-, 2- and 4-letter alphabets and for every piece offset.
-__device__ __forceinline__ uint32_t add_change_reg(Stitch& S, WarpSmem* ws, const ReadKernelParams& P, uint32_t L, uint32_t ridx, const uint8_t* raw,
-                                                   uint32_t ob, uint32_t oe, uint32_t c, uint32_t olen, uint32_t fk, uint32_t fep, uint32_t kb,
-                                                   int lane) {
-  const ChangePlan cp = plan_change(S, L, ob, oe, olen, fk);
+__device__ __forceinline__ uint32_t add_change_reg(Walk& W, WarpSmem* ws, const ReadKernelParams& P, uint32_t ob, uint32_t oe, uint32_t c, uint32_t olen,
+                                                   uint32_t fk, uint32_t fep, uint32_t kb, int lane) {
+  Stitch& S = W.S;
+  const ChangePlan cp = plan_change(S, W.L, ob, oe, olen, fk);
   if (cp.contained) return 0;
   const uint32_t es = cp.es, add = olen - es, tn = cp.re - cp.rs;
   const bool emit = (S.flags & F_EMIT) != 0;
-  uint32_t e_old = S.err_len, c_old = S.cig_len;  // where the flush at the end of this event starts
-  if (emit) {
-    if (cp.gap) {
-      if (cp.gap <= 32u) {
-        if ((uint32_t)lane < cp.gap) ws->errb[(S.err_len + lane) & (RING - 1u)] = raw[cp.gap_src + lane];
-        S.err_len += cp.gap;
-        S.cig_len += cp.gap;  // the CIGAR ring is pre-filled with '='
-      } else {
-        st_save(ws, S);
-        append_cold(smem_addr(ws), P, ridx, raw + cp.gap_src, nullptr, cp.gap, lane);
-        st_load(ws, S);
-        e_old = S.err_len;  // append_cold has flushed its own chunks
-        c_old = S.cig_len;
-        if (st_status(S)) return 0;
-      }
-    }
-    if ((uint32_t)lane >= es && (uint32_t)lane < olen) ws->errb[(S.err_len + lane - es) & (RING - 1u)] = (uint8_t)c;
-    S.err_len += add;
-  }
-  uint32_t ed, nops;
-  if (cp.fast && fk == 4) {  // table alternative against its own key: alignments precomputed at load time
-    const DeviceModels& M = P.M;
-    const uint32_t pi = M.em_piece_begin[fep] + es;
-    const uint32_t o0 = M.em_piece_off[pi];
-    nops = M.em_piece_off[pi + 1] - o0;
-    ed = M.em_piece_edits[pi];
-    if (emit) for (uint32_t x = lane; x < nops; x += 32) ws->cigb[(S.cig_len + x) & (RING - 1u)] = M.em_piece_ops[o0 + x];
-  } else if (cp.fast) {
-    const uint32_t e = fep >= es ? fep - es : 0;    // where the edit sits inside the piece (an edit left of it acts at 0)
-    const bool has_edit = !(fk == 1 && fep < es);   // a substitution in the overlapped part leaves the piece identical
-    uint32_t at = e;                                // where the non-'=' op lands
-    if (fk != 1) {
-      // slide left while the base left of the edit equals the one it would be swapped with
-      const uint32_t kprev = __shfl_up_sync(0xffffffffu, kb, 1);
-      const bool sl = (uint32_t)lane > es && (uint32_t)lane <= es + e && (fk == 2 ? c == kprev : kb == kprev);
-      const uint32_t B = __ballot_sync(0xffffffffu, sl) >> es;
-      at = e - __clz(~(B << (31 - e)));
-    }
-    nops = fk == 2 ? add : tn;  // substitution / deletion: one op per raw base, insertion: one per piece base
-    ed = has_edit ? 1u : 0u;
-    if (emit && has_edit) ws->cigb[(S.cig_len + at) & (RING - 1u)] = fk == 1 ? 'X' : fk == 2 ? 'I' : 'D';
-  } else if ((add == 0 || tn == 0) && add + tn <= 32u) {  // all deletions / all insertions
-    nops = add + tn;
-    ed = nops;
-    if (emit && (uint32_t)lane < nops) ws->cigb[(S.cig_len + lane) & (RING - 1u)] = add == 0 ? 'D' : 'I';
-  } else {
-    uint64_t a = ~0ULL;
-    if (add + tn <= 16u && add != 0 && tn != 0) {
-      const uint32_t qc = __shfl_sync(0xffffffffu, c, (lane - 1 + (int)es) & 31);
-      const uint32_t tc = (uint32_t)lane < tn ? raw[cp.rs + lane] : (uint32_t)'A';
-      a = warp_align_small(qc, add, tc, tn, emit ? ws->cigb : nullptr, S.cig_len, lane);
-    }
-    if (a == ~0ULL) {  // more than 16 ops or a byte outside ACGT: general aligners, ops through the scratch
-      a = align_piece_cold(smem_addr(ws), P, c, es, olen, raw + cp.rs, tn, emit, lane);
-      if (align_status(a)) { st_fail(S, align_status(a)); return 0; }
+  uint32_t ed = 0, nops = 0;
+  bool cold = false;
+  // One emission loop with a single flush site: the unchanged stretch before the change goes out 32 bases per step
+  // (it is usually shorter than that), the piece and its ops go with the last step.
+  uint32_t gap_left = emit ? cp.gap : 0u, gap_src = cp.gap_src;
+  uint32_t e_old, c_old;
+  for (;;) {
+    e_old = S.err_len;
+    c_old = S.cig_len;
+    const uint32_t gn = min(gap_left, 32u);
+    if ((uint32_t)lane < gn) ws->errb[(S.err_len + lane) & (RING - 1u)] = W.raw[gap_src + lane];
+    S.err_len += gn;
+    S.cig_len += gn;  // the CIGAR ring is pre-filled with '='
+    gap_src += gn;
+    gap_left -= gn;
+    if (gap_left == 0) {
       if (emit) {
-        // flush what this event staged so far, then append the ops (possibly more than a ring's worth)
-        if (((e_old ^ S.err_len) | (c_old ^ S.cig_len)) >= CHUNK) st_fail(S, flush_chunks_cold(smem_addr(ws), P, ridx, e_old, S.err_len, c_old, S.cig_len, lane));
-        const uint32_t gwarp = blockIdx.x * WARPS_PER_BLOCK + (threadIdx.x >> 5);
-        const uint8_t* fwd = P.sc_ops + (uint64_t)gwarp * P.sc_ops_cap + P.sc_ops_cap / 2;
-        st_save(ws, S);
-        append_cold(smem_addr(ws), P, ridx, nullptr, fwd, align_nops(a), lane);
-        st_load(ws, S);
+        if ((uint32_t)lane >= es && (uint32_t)lane < olen) ws->errb[(S.err_len + lane - es) & (RING - 1u)] = (uint8_t)c;
+        S.err_len += add;
       }
-      S.ledit += align_edits(a);
-      return align_edits(a);
+      if (cp.fast && fk == 4) {  // table alternative against its own key: alignments precomputed at load time
+        const DeviceModels& M = P.M;
+        const uint32_t pi = M.em_piece_begin[fep] + es;
+        const uint32_t o0 = M.em_piece_off[pi];
+        nops = M.em_piece_off[pi + 1] - o0;
+        ed = M.em_piece_edits[pi];
+        if (emit) for (uint32_t x = lane; x < nops; x += 32) ws->cigb[(S.cig_len + x) & (RING - 1u)] = M.em_piece_ops[o0 + x];
+      } else if (cp.fast) {
+        const uint32_t e = fep >= es ? fep - es : 0;    // where the edit sits inside the piece (an edit left of it acts at 0)
+        const bool has_edit = !(fk == 1 && fep < es);   // a substitution in the overlapped part leaves the piece identical
+        uint32_t at = e;                                // where the non-'=' op lands
+        if (fk != 1) {
+          // slide left while the base left of the edit equals the one it would be swapped with
+          const uint32_t kprev = __shfl_up_sync(0xffffffffu, kb, 1);
+          const bool sl = (uint32_t)lane > es && (uint32_t)lane <= es + e && (fk == 2 ? c == kprev : kb == kprev);
+          const uint32_t B = __ballot_sync(0xffffffffu, sl) >> es;
+          at = e - __clz(~(B << (31 - e)));
+        }
+        nops = fk == 2 ? add : tn;  // substitution / deletion: one op per raw base, insertion: one per piece base
+        ed = has_edit ? 1u : 0u;
+        if (emit && has_edit) ws->cigb[(S.cig_len + at) & (RING - 1u)] = fk == 1 ? 'X' : fk == 2 ? 'I' : 'D';
+      } else if ((add == 0 || tn == 0) && add + tn <= 32u) {  // all deletions / all insertions
+        nops = add + tn;
+        ed = nops;
+        if (emit && (uint32_t)lane < nops) ws->cigb[(S.cig_len + lane) & (RING - 1u)] = add == 0 ? 'D' : 'I';
+      } else {
+        uint64_t a = ~0ULL;
+        if (add + tn <= 16u && add != 0 && tn != 0) {
+          const uint32_t qc = __shfl_sync(0xffffffffu, c, (lane - 1 + (int)es) & 31);
+          const uint32_t tc = (uint32_t)lane < tn ? W.raw[cp.rs + lane] : (uint32_t)'A';
+          a = warp_align_small(qc, add, tc, tn, emit ? ws->cigb : nullptr, S.cig_len, lane);
+        }
+        if (a == ~0ULL) cold = true;  // more than 16 ops or a byte outside ACGT
+        else {
+          nops = align_nops(a);
+          ed = align_edits(a);
+        }
+      }
+      if (emit && !cold) S.cig_len += nops;
     }
-    nops = align_nops(a);
-    ed = align_edits(a);
+    if (cold) break;
+    if (((e_old ^ S.err_len) | (c_old ^ S.cig_len)) >= CHUNK) st_fail(S, flush_chunks(ws, P, W.ridx, e_old, S.err_len, c_old, S.cig_len, lane));
+    if (gap_left == 0) break;
   }
-  if (emit) {
-    S.cig_len += nops;
-    if (((e_old ^ S.err_len) | (c_old ^ S.cig_len)) >= CHUNK) st_fail(S, flush_chunks_cold(smem_addr(ws), P, ridx, e_old, S.err_len, c_old, S.cig_len, lane));
+  if (cold) {
+    walk_save(ws, W);
+    ed = align_piece_cold(smem_addr(ws), lane, P, c, es, olen, cp.rs, tn, e_old, c_old);
+    walk_load(ws, W);
+    return ed;
   }
   S.ledit += ed;
   return ed;
@@ -500,69 +519,78 @@ __device__ __forceinline__ void process_read(const ReadKernelParams& P, WarpSmem
   const DeviceModels& M = P.M;
   const uint32_t k = M.k;
   const uint32_t ws32 = smem_addr(ws);
-  WarpRng rng;
-  rng.seed(P.descs[ridx].seed, ws, lane);
-
-  uint8_t* raw = P.raw + P.raw_off[ridx];
-  StageOut so = stage_assemble(ws32, rng.off, lane, P, ridx, raw);
-  rng.off = so.off;
-  const uint32_t L = (uint32_t)so.value;
-
-  Stitch S;
-  S.err_len = S.cig_len = 0;
-  S.pos_in_raw = 0;
-  S.real_edit = 0;
-  S.flags = 0;
-  S.le = S.lee = S.ledit = 0;
+  Walk W;
+  {
+    WarpRng rng;
+    rng.seed(P.descs[ridx].seed, ws, lane);
+    uint8_t* raw = P.raw + P.raw_off[ridx];
+    StageOut so = stage_assemble(ws32, rng.off, lane, P, ridx, raw);
+    W.off = so.off;
+    W.L = (uint32_t)so.value;
+    W.raw = raw;
+  }
+  W.ridx = ridx;
+  W.pos = 0;
+  W.gbegin = ~0u;
+  W.S.err_len = W.S.cig_len = 0;
+  W.S.pos_in_raw = 0;
+  W.S.real_edit = 0;
+  W.S.flags = 0;
+  W.S.le = W.S.lee = W.S.ledit = 0;
   __syncwarp();
-  ws->st[ST_L] = L;
   ws->st[ST_CAP] = (uint32_t)(P.out_off[ridx + 1] - P.out_off[ridx]);
   if (lane < (int)(RING / 16)) *reinterpret_cast<uint4*>(&ws->cigb[16 * lane]) = eq16();
   __syncwarp();
 
   // ---- K3: error::sequence (src/simulate/error.rs:201-217) ----
-  double target = (1.0 - P.descs[ridx].identity) * (double)L;  // number_of_edit, error.rs:196-198
-  uint32_t gbegin = ~0u;  // raw position of the next glitch
+  W.target = (1.0 - P.descs[ridx].identity) * (double)W.L;  // number_of_edit, error.rs:196-198
   if (M.has_distance) {
     const uint32_t gwarp = blockIdx.x * WARPS_PER_BLOCK + (threadIdx.x >> 5);
-    so = stage_glitches(ws32, rng.off, lane, P, gwarp, L);
-    rng.off = so.off;
-    st_fail(S, so.status);
+    const StageOut so = stage_glitches(ws32, W.off, lane, P, gwarp, W.L);
+    W.off = so.off;
+    st_fail(W.S, so.status);
     __syncwarp();
     ws->st[ST_G] = 0;
     ws->st[ST_NG] = (uint32_t)so.value;
-    if (so.value) gbegin = (uint32_t)P.sc_grec[(uint64_t)gwarp * P.sc_grec_cap].begin;
+    if (so.value) W.gbegin = (uint32_t)P.sc_grec[(uint64_t)gwarp * P.sc_grec_cap].begin;
   }
 
   // add_error (error.rs:267-302): one Bernoulli(target / (L - pos)) per position.  32 positions are
   // tried at once against the current target; the first lane with an event wins.
-  if (st_status(S) == ST_OK) {
-    uint32_t pos = 0;
-    while (pos < L - k) {
-      rng.need(64 + 32);  // 64 words for the 32 positions + spare for the draws of the event (WarpRng hot draws)
-      const uint32_t pi = pos + (uint32_t)lane;
-      const bool inb = pi < L - k;
-      const double rem = (double)(L - pi);
-      const bool brk = target < 0.0 || target > rem;
-      const bool gl = (pi == gbegin) && !(lane == 0 && (S.flags & F_GLITCH_CHECKED));
-      const double p = target / rem;
+  if (st_status(W.S) == ST_OK) {
+    while (W.pos < W.L - k) {
+      if (W.off + 64 + HOT_FIRST > RNG_WORDS || (W.S.flags & F_REPLAY)) {  // 64 words for the 32 positions + the first attempts of an event's draws
+        const bool replay = (W.S.flags & F_REPLAY) != 0;
+        W.S.flags &= ~F_REPLAY;
+        walk_save(ws, W);
+        walk_refill(ws32, lane);
+        walk_load(ws, W);
+        if (replay) W.S.flags |= F_REPLAYED;  // remembered until the replayed event completes
+      }
+      const uint32_t pi = W.pos + (uint32_t)lane;
+      const bool inb = pi < W.L - k;
+      const double rem = (double)(W.L - pi);
+      const bool brk = W.target < 0.0 || W.target > rem;
+      const bool gl = (pi == W.gbegin) && !(lane == 0 && (W.S.flags & F_GLITCH_CHECKED));
+      const double p = W.target / rem;
       const bool one = (p == 1.0);
-      const uint64_t v = rng.peek64_at(rng.off + 2 * (uint32_t)lane);
+      const uint32_t wo = W.off + 2 * (uint32_t)lane;
+      const uint64_t v = (uint64_t)ws->rng[wo] | ((uint64_t)ws->rng[wo + 1] << 32);
       const bool hit = one || v < bernoulli_threshold(p);
       const uint32_t m_any = __ballot_sync(0xffffffffu, !inb || gl || brk || hit);
       if (m_any == 0) {
-        pos += 32;
-        rng.off += 64;
-        S.flags &= ~F_GLITCH_CHECKED;
+        W.pos += 32;
+        W.off += 64;
+        W.S.flags &= ~F_GLITCH_CHECKED;
         continue;
       }
       const int f = __ffs(m_any) - 1;
       const uint32_t fl = (inb ? 1u : 0u) | (gl ? 2u : 0u) | (brk ? 4u : 0u) | (one ? 8u : 0u);
       const uint32_t ff = __shfl_sync(0xffffffffu, fl, f);
       if (f > 0) {
-        pos += (uint32_t)f;
-        rng.off += 2 * (uint32_t)f;
-        S.flags &= ~F_GLITCH_CHECKED;
+        W.pos += (uint32_t)f;
+        W.off += 2 * (uint32_t)f;
+        W.S.flags &= ~F_GLITCH_CHECKED;
       }
       if (!(ff & 1u)) break;  // pos == L - k
       uint32_t edits;
@@ -572,19 +600,20 @@ __device__ __forceinline__ void process_read(const ReadKernelParams& P, WarpSmem
         const GlitchRec* grec = P.sc_grec + (uint64_t)gwarp * P.sc_grec_cap;
         const uint32_t g = ws->st[ST_G];
         const GlitchRec gr = grec[g];
-        gbegin = (g + 1 < ws->st[ST_NG]) ? (uint32_t)grec[g + 1].begin : ~0u;
-        st_save(ws, S);
+        W.gbegin = (g + 1 < ws->st[ST_NG]) ? (uint32_t)grec[g + 1].begin : ~0u;
+        walk_save(ws, W);
         ws->st[ST_G] = g + 1;
-        edits = add_change_cold(ws32, P, ridx, raw, (uint32_t)gr.begin, (uint32_t)gr.end,
-                                P.sc_gseq + (uint64_t)gwarp * P.sc_gseq_cap + gr.seq_off, gr.seq_len, lane);
-        st_load(ws, S);
-        S.flags |= F_GLITCH_CHECKED;  // same pos again, with the new target, glitch check done
+        edits = add_change_cold(ws32, lane, P, (uint32_t)gr.begin, (uint32_t)gr.end, P.sc_gseq + (uint64_t)gwarp * P.sc_gseq_cap + gr.seq_off, gr.seq_len);
+        walk_load(ws, W);
+        W.S.flags |= F_GLITCH_CHECKED;  // same pos again, with the new target, glitch check done
       } else {
         if (ff & 4u) break;  // error.rs:289-291
-        if (!(ff & 8u)) rng.off += 2;
+        const uint32_t off_ev = W.off;  // where a replay of this event starts
+        if (!(ff & 8u)) W.off += 2;
         // Error::add_errors_to_kmer (src/model/error.rs:93-107): the altered k-mer is built in registers, lane i = byte i
-        const uint32_t kb = (uint32_t)lane < k ? (uint32_t)raw[pos + lane] : 0u;
+        const uint32_t kb = (uint32_t)lane < k ? (uint32_t)W.raw[W.pos + lane] : 0u;
         uint32_t c = 0, olen, fk, fep;
+        bool ok = true;
         int key = -1;
         if (M.em_index) {  // 2-bit code of the k-mer; any byte outside ACGT misses the table
           uint32_t part = 0, bad = 0;
@@ -596,30 +625,38 @@ __device__ __forceinline__ void process_read(const ReadKernelParams& P, WarpSmem
           uint32_t code = __reduce_or_sync(0xffffffffu, part);
           if (!__any_sync(0xffffffffu, bad)) key = M.em_index[code];
         }
-        if (key >= 0) {
-          so = stage_alt_from_table(ws32, rng.off, lane, M, key);
-          rng.off = so.off;
-          olen = (uint32_t)so.value;
+        if (key >= 0) {  // one WeightedIndex draw over the alternatives of the k-mer (src/model/error.rs:96-100)
+          const uint32_t a0 = M.em_alt_begin[key], na = M.em_alt_begin[key + 1] - a0;
+          const uint64_t v2 = (uint64_t)ws->rng[W.off] | ((uint64_t)ws->rng[W.off + 1] << 32);  // first attempt: resident (HOT_FIRST)
+          W.off += 2;
+          const double chosen = u64_to_unit12(v2) * M.em_scale[key] + 0.0;
+          uint32_t idx = 0;  // number of partial sums <= chosen among the first na - 1
+          for (uint32_t b = 0; b + 1 < na; b += 32) {
+            const uint32_t i = b + lane;
+            const bool le = (i + 1 < na) && (M.em_cum[a0 + i] <= chosen);
+            idx += __popc(__ballot_sync(0xffffffffu, le));
+          }
           fk = 4;
-          fep = so.status;
+          fep = a0 + idx;  // global id of the chosen alternative (it indexes the precomputed alignments)
           const uint32_t o0 = M.em_alt_off[fep];
+          olen = M.em_alt_off[fep + 1] - o0;
           if (olen <= 32u) {
             if ((uint32_t)lane < olen) c = M.em_alt_bytes[o0 + lane];
-            edits = add_change_reg(S, ws, P, L, ridx, raw, pos, pos + k, c, olen, fk, fep, kb, lane);
+            edits = add_change_reg(W, ws, P, W.pos, W.pos + k, c, olen, fk, fep, kb, lane);
           } else {  // an alternative longer than a warp: through memory
-            st_save(ws, S);
-            edits = add_change_cold(ws32, P, ridx, raw, pos, pos + k, M.em_alt_bytes + o0, olen, lane);
-            st_load(ws, S);
+            walk_save(ws, W);
+            edits = add_change_cold(ws32, lane, P, W.pos, W.pos + k, M.em_alt_bytes + o0, olen);
+            walk_load(ws, W);
           }
         } else {  // random_error (src/model/error.rs:116-135)
-          const uint32_t ep = rng.gen_index_hot(k);
-          const uint32_t kind = rng.gen_range_u32_hot(1, 3);  // 1 substitution, 2 insertion, 3 deletion
+          const uint32_t ep = hot_index(ws, W.off, ok, k);
+          const uint32_t kind = ok ? hot_range_u32(ws, W.off, ok, 1, 3) : 1u;  // 1 substitution, 2 insertion, 3 deletion
           if (kind == 1) {
-            const uint32_t nb = rng.random_base_diff_hot(__shfl_sync(0xffffffffu, kb, ep));
+            const uint32_t nb = ok ? hot_base_diff(ws, W.off, ok, __shfl_sync(0xffffffffu, kb, ep)) : 0u;
             c = (uint32_t)lane == ep ? nb : kb;
             olen = k;
           } else if (kind == 2) {
-            const uint32_t nb = rng.random_base_diff_hot(256u);
+            const uint32_t nb = ok ? hot_base_diff(ws, W.off, ok, 256u) : 0u;
             const uint32_t kprev = __shfl_up_sync(0xffffffffu, kb, 1);
             c = (uint32_t)lane < ep ? kb : ((uint32_t)lane == ep ? nb : kprev);
             olen = k + 1;
@@ -628,44 +665,47 @@ __device__ __forceinline__ void process_read(const ReadKernelParams& P, WarpSmem
             c = (uint32_t)lane < ep ? kb : knext;
             olen = k - 1;
           }
+          if (!ok) {  // the draws ran past the resident words: refill and replay this event from its Bernoulli draw
+            if (W.S.flags & F_REPLAYED) { st_fail(W.S, ST_RNG_EXHAUSTED); break; }  // > 400 words of rejections in one event
+            W.off = off_ev;
+            W.S.flags |= F_REPLAY;
+            continue;
+          }
           fk = kind;
           fep = ep;
-          edits = add_change_reg(S, ws, P, L, ridx, raw, pos, pos + k, c, olen, fk, fep, kb, lane);
+          edits = add_change_reg(W, ws, P, W.pos, W.pos + k, c, olen, fk, fep, kb, lane);
         }
+        W.S.flags &= ~F_REPLAYED;
       }
-      target -= (double)edits;
-      if (st_status(S)) break;
+      W.target -= (double)edits;
+      if (st_status(W.S)) break;
       if (!is_glitch) {
-        if (target < 0.0 || target > (double)(L - pos)) break;  // error.rs:298-300
-        pos += 1;
-        S.flags &= ~F_GLITCH_CHECKED;
+        if (W.target < 0.0 || W.target > (double)(W.L - W.pos)) break;  // error.rs:298-300
+        W.pos += 1;
+        W.S.flags &= ~F_GLITCH_CHECKED;
       }
     }
   }
 
   // ---- K5: tail of the stitch (error.rs:241-246) ----
-  if (st_status(S) == ST_OK) {
-    if ((S.flags & (F_HAS_LAST | F_EMIT)) == (F_HAS_LAST | F_EMIT)) {
-      S.real_edit += S.ledit;
-      S.pos_in_raw = S.le;
+  if (st_status(W.S) == ST_OK) {
+    if ((W.S.flags & (F_HAS_LAST | F_EMIT)) == (F_HAS_LAST | F_EMIT)) {
+      W.S.real_edit += W.S.ledit;
+      W.S.pos_in_raw = W.S.le;
     }
-    if (S.pos_in_raw < L) {
-      st_save(ws, S);
-      append_cold(ws32, P, ridx, raw + S.pos_in_raw, nullptr, L - S.pos_in_raw, lane);
-      st_load(ws, S);
-    }
-    // the partial last chunks (the chunk past max(len) stays inside the capacity: see flush_chunks)
-    (void)flush_chunks_cold(ws32, P, ridx, S.err_len, S.err_len + CHUNK, S.cig_len, S.cig_len + CHUNK, lane);
+    walk_save(ws, W);
+    walk_finish(ws32, lane, P);
+    walk_load(ws, W);
   }
   __syncwarp();
   if (lane == 0) {
-    const uint32_t status = st_status(S);
-    P.raw_len[ridx] = L;
-    P.err_len[ridx] = status ? 0 : S.err_len;
-    P.cig_len[ridx] = status ? 0 : S.cig_len;
-    P.q_cursor[ridx] = rng.cursor();
-    P.real_id[ridx] = (1.0 - ((double)S.real_edit / (double)L)) * 100.0;  // error.rs:246, mod.rs:289
-    P.status[ridx] = status;
+    const uint32_t status = st_status(W.S);
+    P.raw_len[W.ridx] = W.L;
+    P.err_len[W.ridx] = status ? 0 : W.S.err_len;
+    P.cig_len[W.ridx] = status ? 0 : W.S.cig_len;
+    P.q_cursor[W.ridx] = ws->rng_base + W.off;
+    P.real_id[W.ridx] = (1.0 - ((double)W.S.real_edit / (double)W.L)) * 100.0;  // error.rs:246, mod.rs:289
+    P.status[W.ridx] = status;
   }
 }
 
