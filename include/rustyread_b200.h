@@ -151,6 +151,9 @@ int rr_debug_align(rr_ctx* ctx, const uint8_t* query, uint32_t m, const uint8_t*
                    uint8_t* cigar, uint32_t* cigar_len, uint32_t* edits);
 /* first n 32-bit words of StdRng::seed_from_u64(seed), starting at word `first` */
 int rr_debug_rng_words(rr_ctx* ctx, uint64_t seed, uint64_t first, uint32_t n, uint32_t* out);
+/* parity hook: the walk's division (reciprocal + Newton fast path) against the compiler's IEEE `/` on n pseudo-random
+ * operand pairs of the walk's ranges; *mismatches = number of results that differ in any bit (must be 0) */
+int rr_debug_div_check(rr_ctx* ctx, uint64_t seed, uint64_t n, uint64_t* mismatches);
 /* capacity-planning slack for the next batches (<= 0 keeps it) and the number of re-plans so far: lets a test force
  * the "estimate too small -> re-plan with twice the slack" path */
 int rr_debug_set_slack(rr_ctx* ctx, double slack, uint64_t* replans_so_far);

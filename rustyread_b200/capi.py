@@ -56,6 +56,7 @@ EXPORTS = {
     "rr_stream": (C.c_void_p, [C.c_void_p]),
     "rr_debug_align": (C.c_int, [C.c_void_p, C.c_char_p, C.c_uint32, C.c_char_p, C.c_uint32, C.c_void_p, u32p, u32p]),
     "rr_debug_rng_words": (C.c_int, [C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint32, C.c_void_p]),
+    "rr_debug_div_check": (C.c_int, [C.c_void_p, C.c_uint64, C.c_uint64, u64p]),
     "rr_debug_set_slack": (C.c_int, [C.c_void_p, C.c_double, u64p]),
     "rr_debug_fetch": (C.c_int, [C.c_void_p, C.c_uint64, C.c_int, C.c_void_p, C.c_uint64, u64p]),
 }
@@ -259,6 +260,12 @@ class Context:
         out = np.zeros(n, dtype=np.uint32)
         self._ck(self.lib.dll.rr_debug_rng_words(self.h, seed, first, n, out.ctypes.data))
         return out
+
+    def debug_div_check(self, seed, n):
+        """Number of (dividend, divisor) pairs on which the walk's division differs from IEEE `/` in any bit."""
+        bad = C.c_uint64()
+        self._ck(self.lib.dll.rr_debug_div_check(self.h, seed, n, C.byref(bad)))
+        return bad.value
 
     def debug_set_slack(self, slack=0.0):
         n = C.c_uint64()

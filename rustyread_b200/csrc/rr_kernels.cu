@@ -859,6 +859,46 @@ RR_API int rr_debug_rng_words(rr_ctx* ctx, uint64_t seed, uint64_t first, uint32
   return RR_OK;
 }
 
+// walk_div against the compiler's `/` on pseudo-random operands of the walk's ranges (plus the edges); counts bit mismatches
+__global__ void rr_debug_div_kernel(uint64_t seed, uint64_t n, unsigned long long* mismatches) {
+  unsigned long long bad = 0;
+  for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+    uint64_t x = (i + 1) * 0x9E3779B97F4A7C15ULL + seed;
+    x ^= x >> 30; x *= 0xBF58476D1CE4E5B9ULL; x ^= x >> 27; x *= 0x94D049BB133111EBULL; x ^= x >> 31;
+    const uint32_t r_i = 1u + (uint32_t)(x % 0x7fffffffULL);
+    uint64_t y = x * 0xD6E8FEB86659FD93ULL + 1;
+    y ^= y >> 32;
+    double t;
+    const uint32_t sel = (uint32_t)(y & 7);
+    const double u = (double)(y >> 11) * 1.1102230246251565e-16;  // [0, 1)
+    if (sel == 0) t = 0.0;
+    else if (sel == 1) t = (double)r_i;                         // p == 1
+    else if (sel == 2) t = u * 9.5367431640625e-07;             // tiny targets
+    else if (sel == 3) t = ldexp(u + 0.5, -105 + (int)((y >> 3) % 136));
+    else if (sel == 4) t = (double)r_i * u;                     // p uniform in [0, 1)
+    else if (sel == 5) t = (double)(r_i / 2) + u;               // near one half
+    else t = u * 2147483648.0;
+    const double a = walk_div(t, (double)r_i), b = t / (double)r_i;
+    bad += __double_as_longlong(a) != __double_as_longlong(b);
+  }
+  if (bad) atomicAdd(mismatches, bad);
+}
+
+RR_API int rr_debug_div_check(rr_ctx* ctx, uint64_t seed, uint64_t n, uint64_t* mismatches) {
+  if (!ctx || !mismatches) return RR_ERR_ARG;
+  CK(cudaSetDevice(ctx->device));
+  DevBuf d;
+  ENSURE(d, 16);
+  CK(cudaMemsetAsync(d.p, 0, 16, ctx->stream));
+  rr_debug_div_kernel<<<ctx->n_sm * 8, 256, 0, ctx->stream>>>(seed, n, d.as<unsigned long long>());
+  CK(cudaGetLastError());
+  ctx->launches += 1;
+  CK(cudaMemcpyAsync(mismatches, d.p, 8, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  d.release();
+  return RR_OK;
+}
+
 RR_API int rr_debug_set_slack(rr_ctx* ctx, double slack, uint64_t* replans_so_far) {
   if (!ctx) return RR_ERR_ARG;
   if (slack > 0.0) ctx->initial_slack = slack;

@@ -572,7 +572,7 @@ __device__ __forceinline__ void process_read(const ReadKernelParams& P, WarpSmem
       const double rem = (double)(W.L - pi);
       const bool brk = W.target < 0.0 || W.target > rem;
       const bool gl = (pi == W.gbegin) && !(lane == 0 && (W.S.flags & F_GLITCH_CHECKED));
-      const double p = W.target / rem;
+      const double p = walk_div(W.target, rem);
       const bool one = (p == 1.0);
       const uint32_t wo = W.off + 2 * (uint32_t)lane;
       const uint64_t v = (uint64_t)ws->rng[wo] | ((uint64_t)ws->rng[wo + 1] << 32);
@@ -587,11 +587,9 @@ __device__ __forceinline__ void process_read(const ReadKernelParams& P, WarpSmem
       const int f = __ffs(m_any) - 1;
       const uint32_t fl = (inb ? 1u : 0u) | (gl ? 2u : 0u) | (brk ? 4u : 0u) | (one ? 8u : 0u);
       const uint32_t ff = __shfl_sync(0xffffffffu, fl, f);
-      if (f > 0) {
-        W.pos += (uint32_t)f;
-        W.off += 2 * (uint32_t)f;
-        W.S.flags &= ~F_GLITCH_CHECKED;
-      }
+      W.pos += (uint32_t)f;
+      W.off += 2 * (uint32_t)f;
+      if (f > 0) W.S.flags &= ~F_GLITCH_CHECKED;
       if (!(ff & 1u)) break;  // pos == L - k
       uint32_t edits;
       const bool is_glitch = (ff & 2u) != 0;

@@ -33,6 +33,12 @@ def test_rng_words(orc, ctx, seed, first, n):
     assert np.array_equal(got, want)
 
 
+# ---- the scan's division: reciprocal + Newton fast path vs the compiler's IEEE `/`, bit for bit -------------------
+@pytest.mark.parametrize("seed", [1, 42])
+def test_walk_division_is_ieee_exact(ctx, seed):
+    assert ctx.debug_div_check(seed, 1 << 28) == 0
+
+
 # ---- K4: alignment -----------------------------------------------------------------------------------
 def test_align_goldens(ctx, goldens):  # src/alignment.rs:47-86
     for q, t, e, cigar in goldens["alignment.align"]:
