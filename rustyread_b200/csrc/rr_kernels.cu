@@ -385,17 +385,23 @@ RR_API int rr_set_qscore_model(rr_ctx* ctx, uint32_t max_k, uint64_t n, const ui
     }
   }
   std::vector<uint8_t> sc(scores, scores + n_sc);
-  if (!upload(ctx, ctx->d_q_tab_off, tab_off) || !upload(ctx, ctx->d_q_tab, tab) || !upload(ctx, ctx->d_q_dist_off, dist_off) ||
-      !upload(ctx, ctx->d_q_scores, sc) || !upload(ctx, ctx->d_q_cum, cum) || !upload(ctx, ctx->d_q_scale, scale) || !upload(ctx, ctx->d_q_unit, unit))
+  std::vector<QDist> qd(n);
+  for (uint64_t i = 0; i < n; ++i) {
+    qd[i].d0 = score_off[i];
+    qd[i].nd_unit = (score_off[i + 1] - score_off[i]) | (unit[i] ? 0x80000000u : 0u);
+    qd[i].scale = dist_ok[i] ? scale[i] : 0.0;
+  }
+  if (!upload(ctx, ctx->d_q_tab_off, tab_off) || !upload(ctx, ctx->d_q_tab, tab) || !upload(ctx, ctx->d_q_dist_off, qd) ||
+      !upload(ctx, ctx->d_q_scores, sc) || !upload(ctx, ctx->d_q_cum, cum))
     return fail(ctx, RR_ERR_CUDA, "rr_set_qscore_model: upload failed");
   ctx->Q.max_k = max_k;
+  ctx->Q.n_dist = (uint32_t)n;
+  ctx->Q.n_scores = n_sc;
   ctx->Q.tab_off = ctx->d_q_tab_off.as<uint32_t>();
   ctx->Q.tab = ctx->d_q_tab.as<uint16_t>();
-  ctx->Q.dist_off = ctx->d_q_dist_off.as<uint32_t>();
+  ctx->Q.dist = ctx->d_q_dist_off.as<QDist>();
   ctx->Q.scores = ctx->d_q_scores.as<uint8_t>();
   ctx->Q.cum = ctx->d_q_cum.as<double>();
-  ctx->Q.scale = ctx->d_q_scale.as<double>();
-  ctx->Q.unit = ctx->d_q_unit.as<uint8_t>();
   ctx->have_qscore = true;
   return RR_OK;
 }
@@ -626,7 +632,11 @@ static int enqueue(rr_ctx* ctx, Slot& sl) {
   QP.qual = sl.d_qual.as<uint8_t>();
   QP.status = P.status;
   uint32_t qgrid = (uint32_t)std::min<uint64_t>((uint64_t)ctx->n_sm * 8, n);
-  rr_qscore_kernel<<<qgrid, Q_THREADS, 0, ctx->stream>>>(QP);
+  const bool q_k1 = ctx->Q.max_k == 1, q_cached = ctx->Q.n_dist <= QD_CACHE && ctx->Q.n_scores <= QS_CACHE;
+  if (q_k1 && q_cached) rr_qscore_kernel<true, true><<<qgrid, Q_THREADS, 0, ctx->stream>>>(QP);
+  else if (q_k1) rr_qscore_kernel<true, false><<<qgrid, Q_THREADS, 0, ctx->stream>>>(QP);
+  else if (q_cached) rr_qscore_kernel<false, true><<<qgrid, Q_THREADS, 0, ctx->stream>>>(QP);
+  else rr_qscore_kernel<false, false><<<qgrid, Q_THREADS, 0, ctx->stream>>>(QP);
   CK(cudaGetLastError());
   CK(cudaEventRecord(sl.ev[2], ctx->stream));
   PackKernelParams K{};

@@ -18,16 +18,24 @@ constexpr int Q_THREADS = 256;
 constexpr int Q_PER_THREAD = 8;
 constexpr int Q_TILE = 2040;  // multiple of 8; 2 * 2040 + 15 words fit in 256 ChaCha blocks
 constexpr int Q_HALO = 8;     // (max_k - 1) / 2 <= 7
+constexpr uint32_t QD_CACHE = 128;   // distributions kept in shared memory when the whole model fits (random / ideal / small files)
+constexpr uint32_t QS_CACHE = 2048;  // ... and their scores
+
+// One distribution of the model: where its scores / partial sums start, how many there are (top bit: every weight is
+// exactly 1.0, so the partial sums are 1, 2, 3, ... and the search is a truncation), and the UniformFloat scale.
+struct __align__(16) QDist {
+  uint32_t d0, nd_unit;
+  double scale;
+};
 
 struct QscoreModelDev {
   uint32_t max_k;
+  uint32_t n_dist, n_scores;
   const uint32_t* tab_off;   // indexed by window length l (odd) -> offset into tab
   const uint16_t* tab;       // dist id, 0xFFFF = unknown
-  const uint32_t* dist_off;  // n_dist + 1
+  const QDist* dist;         // n_dist
   const uint8_t* scores;
   const double* cum;         // per dist: partial sums, last = total
-  const double* scale;       // per dist
-  const uint8_t* unit;       // per dist: 1 when every weight is exactly 1.0 (partial sums are 1, 2, 3, ...)
 };
 
 struct QscoreKernelParams {
@@ -46,16 +54,31 @@ struct QscoreKernelParams {
   uint32_t* status;
 };
 
-__device__ __forceinline__ uint32_t cigar_sym(uint8_t c) { return c == '=' ? 0u : c == 'X' ? 1u : c == 'I' ? 2u : 3u; }
+__device__ __forceinline__ uint32_t cigar_sym(uint32_t c) { return c == '=' ? 0u : c == 'X' ? 1u : c == 'I' ? 2u : 3u; }
 
+// K1: max_k == 1 (Quality::random / ideal): the window is the position itself.  CACHED: the whole model sits in shared memory.
+template <bool K1, bool CACHED>
 __global__ void __launch_bounds__(Q_THREADS) rr_qscore_kernel(const __grid_constant__ QscoreKernelParams P) {
-  __shared__ uint32_t s_words[Q_THREADS * 16];
+  __shared__ __align__(16) uint32_t s_words[Q_THREADS * 16];
   __shared__ __align__(16) uint8_t s_cig[Q_HALO + Q_TILE + Q_HALO];
+  __shared__ __align__(16) QDist s_dist[CACHED ? QD_CACHE : 1];
+  __shared__ uint8_t s_scores[CACHED ? QS_CACHE : 1];
   __shared__ uint32_t s_warp_sum[Q_THREADS / 32];
   __shared__ uint32_t s_slot;
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const QscoreModelDev& Q = P.Q;
-  const uint32_t margin = (Q.max_k - 1) / 2;
+  const uint32_t margin = K1 ? 0u : (Q.max_k - 1) / 2;
+  if (CACHED) {
+    for (uint32_t i = tid; i < Q.n_dist; i += Q_THREADS) s_dist[i] = Q.dist[i];
+    for (uint32_t i = tid; i < Q.n_scores; i += Q_THREADS) s_scores[i] = Q.scores[i];
+  }
+  uint32_t dsym0 = 0xFFFFu, dsym1 = 0xFFFFu, dsym2 = 0xFFFFu;  // K1: distribution of '=', 'X', 'I'
+  if (K1) {
+    const uint32_t o = Q.tab_off[1];
+    dsym0 = Q.tab[o];
+    dsym1 = Q.tab[o + 1];
+    dsym2 = Q.tab[o + 2];
+  }
 
   for (;;) {
     __syncthreads();
@@ -65,17 +88,17 @@ __global__ void __launch_bounds__(Q_THREADS) rr_qscore_kernel(const __grid_const
     if (slot >= P.n_reads) break;
     const uint32_t ridx = P.order[slot];
     if (P.status[ridx] != ST_OK) continue;
-    const uint64_t n = P.cig_len[ridx];
+    const uint32_t n = (uint32_t)P.cig_len[ridx];  // < 2^31 (the host refuses longer reads)
     const uint8_t* cig = P.cig + P.out_off[ridx];
     uint8_t* qual = P.qual + P.packed_off[ridx];
-    const uint64_t elen = P.err_len[ridx];
+    const uint32_t elen = (uint32_t)P.err_len[ridx];
     const uint64_t qcur = P.q_cursor[ridx];
     uint32_t key[8];
     chacha_key_from_u64(P.descs[ridx].seed, key);
 
-    uint64_t rank0 = 0;  // non-'D' positions before this tile
-    for (uint64_t t0 = 0; t0 < n; t0 += Q_TILE) {
-      const uint32_t tn = (uint32_t)min((uint64_t)Q_TILE, n - t0);
+    uint32_t rank0 = 0;  // non-'D' positions before this tile
+    for (uint32_t t0 = 0; t0 < n; t0 += Q_TILE) {
+      const uint32_t tn = min((uint32_t)Q_TILE, n - t0);
       __syncthreads();
       // stage the tile (+ halo) of the CIGAR
       // body: one aligned 8-byte load per thread (read offsets are 16-byte aligned, tiles are multiples of 8)
@@ -86,18 +109,21 @@ __global__ void __launch_bounds__(Q_THREADS) rr_qscore_kernel(const __grid_const
         } else {
           for (uint32_t x = p8; x < tn; ++x) s_cig[Q_HALO + x] = cig[t0 + x];
         }
-        if (tid < 2 * Q_HALO) {  // halo: 8 positions before the tile, 8 after
+        if (!K1 && tid < 2 * Q_HALO) {  // halo: 8 positions before the tile, 8 after
           const int64_t gi = tid < Q_HALO ? (int64_t)t0 - Q_HALO + tid : (int64_t)t0 + tn + (tid - Q_HALO);
-          s_cig[tid < Q_HALO ? tid : Q_HALO + tn + (tid - Q_HALO)] = (gi >= 0 && (uint64_t)gi < n) ? cig[gi] : 0;
+          s_cig[tid < Q_HALO ? tid : Q_HALO + tn + (tid - Q_HALO)] = (gi >= 0 && gi < (int64_t)n) ? cig[gi] : 0;
         }
       }
       __syncthreads();
       // rank the non-'D' positions: 8 consecutive positions per thread
       const uint32_t p0 = tid * Q_PER_THREAD;
       uint32_t flags = 0;
+      const uint2 cw = *reinterpret_cast<const uint2*>(s_cig + Q_HALO + p0);  // this thread's 8 ops
 #pragma unroll
-      for (int x = 0; x < Q_PER_THREAD; ++x)
-        if (p0 + x < tn && s_cig[Q_HALO + p0 + x] != 'D') flags |= 1u << x;
+      for (int x = 0; x < Q_PER_THREAD; ++x) {
+        const uint32_t c = ((x < 4 ? cw.x : cw.y) >> (8 * (x & 3))) & 0xffu;
+        if (p0 + x < tn && c != 'D') flags |= 1u << x;
+      }
       uint32_t mine = __popc(flags);
       uint32_t incl = mine;
 #pragma unroll
@@ -110,67 +136,76 @@ __global__ void __launch_bounds__(Q_THREADS) rr_qscore_kernel(const __grid_const
       uint32_t wbase = 0, total = 0;
 #pragma unroll
       for (int w = 0; w < Q_THREADS / 32; ++w) {
-        uint32_t s = s_warp_sum[w];
-        if (w < wid) wbase += s;
-        total += s;
+        uint32_t sw = s_warp_sum[w];
+        if (w < wid) wbase += sw;
+        total += sw;
       }
       const uint32_t excl = wbase + incl - mine;
       // the ChaCha blocks holding words [qcur + 2 rank0, qcur + 2 (rank0 + total))
-      const uint64_t w_first = qcur + 2 * rank0;
+      const uint64_t w_first = qcur + 2 * (uint64_t)rank0;
       const uint64_t b_first = w_first >> 4;
       if (total) {
         const uint64_t b_last = (w_first + 2 * (uint64_t)total - 1) >> 4;
         if (b_first + (uint64_t)tid <= b_last) {
           uint32_t out[16];
           chacha12_block(key, b_first + (uint64_t)tid, out);
+          uint4* dst = reinterpret_cast<uint4*>(s_words + (uint32_t)tid * 16u);
 #pragma unroll
-          for (int j = 0; j < 16; ++j) s_words[rng_swz((uint32_t)tid * 16u + j)] = out[j];
+          for (int j = 0; j < 4; ++j) dst[j] = make_uint4(out[4 * j], out[4 * j + 1], out[4 * j + 2], out[4 * j + 3]);
         }
       }
       __syncthreads();
-      uint32_t r = excl;
+      const bool edge = !K1 && (t0 < margin || t0 + tn + margin > n);  // tiles that touch an end of the read shrink their windows
+      uint32_t woff = (uint32_t)(w_first & 15ULL) + 2 * excl;
+      uint32_t qi = rank0 + excl;
 #pragma unroll
       for (int x = 0; x < Q_PER_THREAD; ++x) {
         if (!(flags & (1u << x))) continue;
-        const uint64_t i = t0 + p0 + x;  // position in the CIGAR
-        // centred window, shrunk symmetrically at both ends (quality.rs:22-34)
-        uint32_t half;
-        if (i < margin) half = (uint32_t)i;
-        else if (i >= n - margin) half = (uint32_t)(n - i - 1);
-        else half = margin;
-        const uint32_t len = 2 * half + 1;
-        const uint8_t* wptr = s_cig + Q_HALO + p0 + x - half;
-        uint32_t code = 0;
-        if (margin == 0) code = cigar_sym(wptr[0]);  // max_k == 1 (Quality::random): the window is the position itself
-        else for (uint32_t y = 0; y < len; ++y) code |= cigar_sym(wptr[y]) << (2 * y);
-        const uint32_t dist = Q.tab[Q.tab_off[len] + code];
-        uint8_t qv = '!';
+        uint32_t dist;
+        if (K1) {
+          const uint32_t c = ((x < 4 ? cw.x : cw.y) >> (8 * (x & 3))) & 0xffu;
+          dist = c == '=' ? dsym0 : c == 'X' ? dsym1 : dsym2;
+        } else {
+          // centred window, shrunk symmetrically at both ends (quality.rs:22-34)
+          uint32_t half = margin;
+          if (edge) {
+            const uint32_t i = t0 + p0 + x;  // position in the CIGAR
+            half = min(margin, min(i, n - i - 1));
+          }
+          const uint32_t len = 2 * half + 1;
+          const uint8_t* wptr = s_cig + Q_HALO + p0 + x - half;
+          uint32_t code = 0;
+          for (uint32_t y = 0; y < len; ++y) code |= cigar_sym(wptr[y]) << (2 * y);
+          dist = Q.tab[Q.tab_off[len] + code];
+        }
+        uint32_t qv = '!';
         if (dist == 0xFFFFu) {
           P.status[ridx] = ST_QUAL;
         } else {
-          const uint32_t woff = (uint32_t)(w_first + 2 * (uint64_t)r - (b_first << 4));
-          const uint64_t v = (uint64_t)s_words[rng_swz(woff)] | ((uint64_t)s_words[rng_swz(woff + 1)] << 32);
-          const uint32_t d0 = Q.dist_off[dist], nd = Q.dist_off[dist + 1] - d0;
-          const double chosen = u64_to_unit12(v) * Q.scale[dist] + 0.0;
-          uint32_t lo = 0, hi = nd - 1;  // partition_point over the first nd - 1 partial sums
-          if (Q.unit[dist]) {
+          const uint64_t v = (uint64_t)s_words[woff] | ((uint64_t)s_words[woff + 1] << 32);
+          const QDist d = CACHED ? s_dist[dist] : Q.dist[dist];
+          const uint32_t hi = (d.nd_unit & 0x7fffffffu) - 1;
+          const double chosen = u64_to_unit12(v) * d.scale + 0.0;
+          uint32_t lo = 0;  // partition_point over the first nd - 1 partial sums
+          if (d.nd_unit >> 31) {
             lo = min((uint32_t)chosen, hi);  // partial sums are exactly 1, 2, ..: #{i : i + 1 <= chosen} = floor(chosen)
           } else {
-            while (lo < hi) {
-              uint32_t mid = (lo + hi) >> 1;
-              if (Q.cum[d0 + mid] <= chosen) lo = mid + 1; else hi = mid;
+            uint32_t up = hi;
+            while (lo < up) {
+              uint32_t mid = (lo + up) >> 1;
+              if (Q.cum[d.d0 + mid] <= chosen) lo = mid + 1; else up = mid;
             }
           }
-          qv = Q.scores[d0 + lo] + 33;
+          qv = (CACHED ? s_scores[d.d0 + lo] : Q.scores[d.d0 + lo]) + 33u;
         }
-        const uint64_t qi = rank0 + r;
-        if (qi < elen) qual[qi] = qv;
-        ++r;
+        if (qi < elen) qual[qi] = (uint8_t)qv;
+        woff += 2;
+        ++qi;
       }
       rank0 += total;
     }
     // mod.rs:284-287: the quality string is resized to the sequence length with '!'
-    for (uint64_t x = rank0 + tid; x < elen; x += Q_THREADS) qual[x] = '!';
+    for (uint32_t x = rank0 + tid; x < elen; x += Q_THREADS) qual[x] = '!';
   }
 }
 
