@@ -162,7 +162,7 @@ __global__ void __launch_bounds__(Q_THREADS) rr_qscore_kernel(const __grid_const
       for (int x = 0; x < Q_PER_THREAD; ++x) {
         if (!(flags & (1u << x))) continue;
         uint32_t dist;
-        if (K1) {
+        if constexpr (K1) {
           const uint32_t c = ((x < 4 ? cw.x : cw.y) >> (8 * (x & 3))) & 0xffu;
           dist = c == '=' ? dsym0 : c == 'X' ? dsym1 : dsym2;
         } else {
@@ -170,7 +170,12 @@ __global__ void __launch_bounds__(Q_THREADS) rr_qscore_kernel(const __grid_const
           uint32_t half = margin;
           if (edge) {
             const uint32_t i = t0 + p0 + x;  // position in the CIGAR
-            half = min(margin, min(i, n - i - 1));
+            if (i < margin) half = i;
+            else if (i >= n - margin) half = n - i - 1;  // wraps like the reference's usize when n < margin
+            if (i < half || i + half + 1 > n) {          // the slice cigar[start..end] is out of range: the reference panics
+              P.status[ridx] = ST_REF_PANIC;
+              half = 0;
+            }
           }
           const uint32_t len = 2 * half + 1;
           const uint8_t* wptr = s_cig + Q_HALO + p0 + x - half;
