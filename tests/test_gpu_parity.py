@@ -273,6 +273,58 @@ def test_synthetic_badread_scale_models(orc):
     ctx.close()
 
 
+def _long_alt_model(k, seed=5):
+    """Every k-mer in the table; alternatives of 0..64 bytes (longer than a warp: the memory path of add_change), several edits."""
+    rnd = random.Random(seed)
+    lines = []
+    for code in range(4 ** k):
+        kmer = "".join("ACGT"[(code >> (2 * (k - 1 - i))) & 3] for i in range(k))
+        alts = []
+        na = rnd.randint(1, 6)
+        for _ in range(na):
+            r = rnd.random()
+            if r < 0.15:
+                a = "".join(rnd.choice("ACGT") for _ in range(rnd.randint(33, 64)))  # through memory
+            elif r < 0.3:
+                a = kmer[: rnd.randint(0, k - 1)]  # a prefix (possibly empty): all deletions
+            elif r < 0.45:
+                a = kmer + "".join(rnd.choice("ACGT") for _ in range(rnd.randint(8, 24)))  # more than 16 ops: the mid-size aligner
+            else:
+                a = list(kmer)
+                a[rnd.randrange(k)] = rnd.choice("ACGT")
+                a.insert(rnd.randrange(k), rnd.choice("ACGT"))
+                a = "".join(a)
+            alts.append("%s,%s" % (a, repr(round(0.9 / na, 6))))
+        lines.append("%s,0.05;%s;" % (kmer, ";".join(alts)))
+    return "\n".join(lines) + "\n"
+
+
+@pytest.mark.parametrize("k", [3, 5])
+def test_table_alternatives_longer_than_a_warp_and_other_k(orc, k):
+    fasta = helpers.random_fasta(orc, [120_000])
+    spec = dict(error_model=_long_alt_model(k), length=(4000.0, 3000.0), identity=(80.0, 95.0, 6.0), glitch=(800.0, 30.0, 30.0))
+    _, ctx, batch, n = _run_pair(orc, fasta, spec, 600_000)
+    ctx.close()
+
+
+def test_reference_with_bytes_outside_acgt(orc):
+    # N runs, IUPAC codes and lower case pass through untouched (src/references.rs:162-166); k-mers that contain them miss the
+    # error-model table and alignments that meet them leave the register aligner for the general one
+    fasta = helpers.random_fasta(orc, [150_000])
+    rnd = random.Random(3)
+    lines = fasta.split("\n")
+    for i in range(1, len(lines)):
+        if lines[i] and rnd.random() < 0.2:
+            row = list(lines[i])
+            for _ in range(rnd.randint(1, 6)):
+                row[rnd.randrange(len(row))] = rnd.choice("NnRYacgtKMW")
+            lines[i] = "".join(row)
+    error_text, qscore_text = _synthetic_models()
+    for spec in (dict(length=(6000.0, 5000.0)), dict(error_model=error_text, qscore_model=qscore_text, length=(6000.0, 5000.0))):
+        _, ctx, batch, n = _run_pair(orc, "\n".join(lines), spec, 900_000)
+        ctx.close()
+
+
 def test_ideal_qscore_and_no_glitch_no_adapter(orc):
     fasta = helpers.random_fasta(orc, [200_000])
     spec = dict(qscore_model="ideal", glitch=(0.0, 0.0, 0.0), adapter=("", "", 0.0, 0.0, 0.0, 0.0), rates=(0.0, 0.0, 0.0),
