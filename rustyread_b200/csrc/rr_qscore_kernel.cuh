@@ -54,8 +54,6 @@ struct QscoreKernelParams {
   uint32_t* status;
 };
 
-__device__ __forceinline__ uint32_t cigar_sym(uint32_t c) { return c == '=' ? 0u : c == 'X' ? 1u : c == 'I' ? 2u : 3u; }
-
 // K1: max_k == 1 (Quality::random / ideal): the window is the position itself.  CACHED: the whole model sits in shared memory.
 template <bool K1, bool CACHED>
 __global__ void __launch_bounds__(Q_THREADS) rr_qscore_kernel(const __grid_constant__ QscoreKernelParams P) {
@@ -156,6 +154,23 @@ __global__ void __launch_bounds__(Q_THREADS) rr_qscore_kernel(const __grid_const
       }
       __syncthreads();
       const bool edge = !K1 && (t0 < margin || t0 + tn + margin > n);  // tiles that touch an end of the read shrink their windows
+      // The 2-bit symbols ('=' 0, 'X' 1, 'I' 2, 'D' / outside the read 3) of ops p0 - 8 .. p0 + 15, 4 bytes at a time: with
+      // '=' 0x3D, 'X' 0x58, 'I' 0x49, 'D' 0x44 the symbol is (~bit4, ~bit0) of the byte.  A window is then a shift and a mask.
+      uint64_t syms = 0;
+      if (!K1) {
+        const uint2* wp = reinterpret_cast<const uint2*>(s_cig + Q_HALO + p0 - 8);
+#pragma unroll
+        for (int g = 0; g < 3; ++g) {
+          const uint2 w2 = wp[g];
+#pragma unroll
+          for (int h2 = 0; h2 < 2; ++h2) {
+            const uint32_t y = ~(h2 ? w2.y : w2.x);
+            const uint32_t b = (y & 0x01010101u) | ((y >> 3) & 0x02020202u);  // one symbol in the low 2 bits of every byte
+            const uint32_t pk = (b | (b >> 6) | (b >> 12) | (b >> 18)) & 0xffu;
+            syms |= (uint64_t)pk << (8 * (2 * g + h2));
+          }
+        }
+      }
       uint32_t woff = (uint32_t)(w_first & 15ULL) + 2 * excl;
       uint32_t qi = rank0 + excl;
 #pragma unroll
@@ -178,9 +193,8 @@ __global__ void __launch_bounds__(Q_THREADS) rr_qscore_kernel(const __grid_const
             }
           }
           const uint32_t len = 2 * half + 1;
-          const uint8_t* wptr = s_cig + Q_HALO + p0 + x - half;
-          uint32_t code = 0;
-          for (uint32_t y = 0; y < len; ++y) code |= cigar_sym(wptr[y]) << (2 * y);
+          // ops p0 + x - half .. p0 + x + half = symbols 8 + x - half .. of the thread's 24-symbol word
+          const uint32_t code = (uint32_t)(syms >> (2 * (8 + x - half))) & ((1u << (2 * len)) - 1u);
           dist = Q.tab[Q.tab_off[len] + code];
         }
         uint32_t qv = '!';
