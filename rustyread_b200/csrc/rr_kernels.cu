@@ -84,6 +84,7 @@ struct rr_ctx {
     double slack = 1.5;
     uint64_t sc_grec_cap = 0, sc_gseq_cap = 0;
     uint32_t read_grid = 0;
+    uint32_t n_heavy = 0, n_fast_sms = 0, fast_stride = 1;  // fast lanes of the read kernel (ReadKernelParams)
     DevBuf d_descs, d_order, d_queue, d_raw_off, d_out_off;
     DevBuf d_raw_len, d_err_len, d_cig_len, d_q_cursor, d_real_id, d_status, d_packed_off, d_totals;
     DevBuf d_seq, d_qual;
@@ -107,6 +108,9 @@ struct rr_ctx {
 
 // RR_TRACE=1: host-side timeline of the batch pipeline on stderr (developer aid, off by default)
 static const bool g_trace = std::getenv("RR_TRACE") != nullptr;
+static const uint32_t g_fast_warps = std::getenv("RR_FAST_WARPS") ? (uint32_t)std::atoi(std::getenv("RR_FAST_WARPS")) : 4u;
+static const double g_fast_threshold = std::getenv("RR_FAST_THRESHOLD") ? std::atof(std::getenv("RR_FAST_THRESHOLD")) : 0.7;
+static const bool g_no_fast_lanes = std::getenv("RR_NO_FAST_LANES") != nullptr;  // developer aid: A/B of the read kernel's fast lanes
 static void trace(const char* what, uint64_t batch) {
   if (!g_trace) return;
   timespec ts;
@@ -514,6 +518,23 @@ static int plan(rr_ctx* ctx, Slot& sl) {
   }
   std::iota(sl.h_order.begin(), sl.h_order.end(), 0u);
   std::stable_sort(sl.h_order.begin(), sl.h_order.end(), [&](uint32_t a, uint32_t b) { return work[a] > work[b]; });
+  // Fast lanes: reads that hold more than 0.7 of a warp's share of the batch's work would set the kernel's length at the
+  // issue rate of a fully occupied scheduler; enough half-occupancy SMs take them to run each at about twice that rate.
+  {
+    const double n_warps = (double)ctx->n_sm * RR_BLOCKS_PER_SM * WARPS_PER_BLOCK;
+    double total = 0;
+    for (uint64_t i = 0; i < n; ++i) total += work[i];
+    const double share = total / n_warps;
+    uint64_t nh = 0;
+    double heavy = 0;
+    while (nh < n && work[sl.h_order[nh]] > g_fast_threshold * share) heavy += work[sl.h_order[nh++]];
+    const uint32_t max_fast = (uint32_t)std::max(1, ctx->n_sm / 6);
+    uint32_t nf = nh ? (uint32_t)std::min<double>(max_fast, std::ceil(heavy / (0.4 * (WARPS_PER_BLOCK / (double)g_fast_warps) * share) / (RR_BLOCKS_PER_SM * g_fast_warps))) : 0;
+    if (g_no_fast_lanes || n < (uint64_t)n_warps) nf = 0;  // fewer reads than warps: the batch is latency-bound whatever is done
+    sl.n_fast_sms = nf;
+    sl.n_heavy = nf ? (uint32_t)nh : 0;
+    sl.fast_stride = nf ? (uint32_t)std::max(1, ctx->n_sm / (int)nf) : 1;
+  }
   sl.sc_grec_cap = (uint64_t)max_ng + 8;
   sl.sc_gseq_cap = align16((uint64_t)(max_ng * (ctx->glitch_mean_size + 1.0)) + 64);
   return RR_OK;
@@ -593,6 +614,10 @@ static int enqueue(rr_ctx* ctx, Slot& sl) {
   P.order = sl.d_order.as<uint32_t>();
   P.n_reads = n;
   P.queue = sl.d_queue.as<uint32_t>();
+  P.n_heavy = sl.n_heavy;
+  P.n_fast_sms = sl.n_fast_sms;
+  P.fast_stride = sl.fast_stride;
+  P.fast_warps = g_fast_warps;
   P.raw_off = sl.d_raw_off.as<uint64_t>();
   P.out_off = sl.d_out_off.as<uint64_t>();
   P.raw = ctx->d_raw.as<uint8_t>();

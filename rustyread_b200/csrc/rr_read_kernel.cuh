@@ -711,12 +711,32 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, RR_BLOCKS_PER_SM) rr_rea
   __shared__ WarpSmem smem[WARPS_PER_BLOCK];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   WarpSmem* ws = &smem[warp];
+  // fast-lane SMs (see ReadKernelParams): a wrong guess about the numbering of the SMs only changes who takes which read
+  bool fast = false;
+  if (P.n_fast_sms) {
+    uint32_t smid;
+    asm("mov.u32 %0, %%smid;" : "=r"(smid));
+    fast = smid % P.fast_stride == 0 && smid / P.fast_stride < P.n_fast_sms;
+    if (fast && (uint32_t)warp >= P.fast_warps) return;
+  }
+  bool first_open = true;  // the queue this warp prefers still has entries
   for (;;) {
-    uint32_t slot = 0;
-    if (lane == 0) slot = atomicAdd(P.queue, 1u);
-    slot = __shfl_sync(0xffffffffu, slot, 0);
-    if (slot >= P.n_reads) break;
-    process_read(P, ws, P.order[slot], lane);
+    uint32_t slot = ~0u;
+    if (lane == 0) {
+      // fast lanes: heavy reads first, then the rest; the others: the rest first, then whatever heavy reads are left
+      if (first_open) {
+        slot = fast ? atomicAdd(P.queue + 2, 1u) : P.n_heavy + atomicAdd(P.queue, 1u);
+        if (slot >= (fast ? P.n_heavy : P.n_reads)) slot = ~0u;
+      }
+      if (slot == ~0u) {
+        slot = fast ? P.n_heavy + atomicAdd(P.queue, 1u) : atomicAdd(P.queue + 2, 1u);
+        if (slot >= (fast ? P.n_reads : P.n_heavy)) slot = ~0u;
+      }
+    }
+    const uint32_t got = __shfl_sync(0xffffffffu, slot, 0);
+    if (got == ~0u) break;
+    if (fast ? got >= P.n_heavy : got < P.n_heavy) first_open = false;
+    process_read(P, ws, P.order[got], lane);
     __syncwarp();
   }
 }
