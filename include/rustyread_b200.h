@@ -135,6 +135,17 @@ int rr_download(rr_ctx* ctx, rr_batch* out);
 int rr_submit(rr_ctx* ctx, uint64_t n, const rr_desc* descs);
 int rr_collect(rr_ctx* ctx, rr_batch* out);
 
+/* Streaming form of rr_collect for a caller that consumes the batch read by read, as the FASTQ writer does
+ * (mod.rs:191-212): the oldest submitted batch is handed over in consecutive parts of about 32 MiB of sequence through a
+ * ring of three small pinned buffers, so no whole-batch pinned staging is allocated (page-locking gigabytes costs
+ * seconds) and the D2H of part p + 1 runs while the caller formats part p.
+ *   rr_collect_begin  waits for the batch's kernels; *n_reads = reads of the batch
+ *   rr_collect_part   next part: an rr_batch whose read 0 is read *first of the batch (offsets relative to the part's
+ *                     arenas); valid until the next rr_collect_part.  part->n_reads == 0: the batch is finished and
+ *                     counts as collected. */
+int rr_collect_begin(rr_ctx* ctx, uint64_t* n_reads, uint64_t* total_bases);
+int rr_collect_part(rr_ctx* ctx, rr_batch* part, uint64_t* first);
+
 /* number of kernel launches issued by this context so far, and device milliseconds spent in the
  * last rr_run (CUDA events on the context's stream): [0] whole run, [1] read kernel (assemble +
  * glitches + error walk + alignment + stitch), [2] qscore kernel, [3] pack kernels */
@@ -156,6 +167,8 @@ int rr_debug_rng_words(rr_ctx* ctx, uint64_t seed, uint64_t first, uint32_t n, u
 int rr_debug_div_check(rr_ctx* ctx, uint64_t seed, uint64_t n, uint64_t* mismatches);
 /* capacity-planning slack for the next batches (<= 0 keeps it) and the number of re-plans so far: lets a test force
  * the "estimate too small -> re-plan with twice the slack" path */
+/* size of the parts of the streaming drain (default 32 MiB), so that tests can force many parts on a small batch */
+int rr_debug_set_part_bytes(rr_ctx* ctx, uint64_t bytes);
 int rr_debug_set_slack(rr_ctx* ctx, double slack, uint64_t* replans_so_far);
 /* intermediate products of the last rr_run for read i: which = 0 raw fragment, 1 CIGAR */
 int rr_debug_fetch(rr_ctx* ctx, uint64_t i, int which, uint8_t* out, uint64_t cap, uint64_t* len);

@@ -50,6 +50,8 @@ EXPORTS = {
     "rr_download": (C.c_int, [C.c_void_p, C.POINTER(rr_batch)]),
     "rr_submit": (C.c_int, [C.c_void_p, C.c_uint64, C.c_void_p]),
     "rr_collect": (C.c_int, [C.c_void_p, C.POINTER(rr_batch)]),
+    "rr_collect_begin": (C.c_int, [C.c_void_p, u64p, u64p]),
+    "rr_collect_part": (C.c_int, [C.c_void_p, C.POINTER(rr_batch), u64p]),
     "rr_kernel_launches": (C.c_uint64, [C.c_void_p]),
     "rr_last_run_ms": (C.c_int, [C.c_void_p, C.POINTER(C.c_float)]),
     "rr_last_run_bases": (C.c_uint64, [C.c_void_p]),
@@ -57,6 +59,7 @@ EXPORTS = {
     "rr_debug_align": (C.c_int, [C.c_void_p, C.c_char_p, C.c_uint32, C.c_char_p, C.c_uint32, C.c_void_p, u32p, u32p]),
     "rr_debug_rng_words": (C.c_int, [C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint32, C.c_void_p]),
     "rr_debug_div_check": (C.c_int, [C.c_void_p, C.c_uint64, C.c_uint64, u64p]),
+    "rr_debug_set_part_bytes": (C.c_int, [C.c_void_p, C.c_uint64]),
     "rr_debug_set_slack": (C.c_int, [C.c_void_p, C.c_double, u64p]),
     "rr_debug_fetch": (C.c_int, [C.c_void_p, C.c_uint64, C.c_int, C.c_void_p, C.c_uint64, u64p]),
 }
@@ -238,6 +241,18 @@ class Context:
         self._ck(self.lib.dll.rr_collect(self.h, C.byref(b)))
         return Batch(b)
 
+    def collect_parts(self):
+        """Streaming form of collect(): yields (first_read, Batch) for consecutive parts of the oldest submitted batch."""
+        n, bases = C.c_uint64(), C.c_uint64()
+        self._ck(self.lib.dll.rr_collect_begin(self.h, C.byref(n), C.byref(bases)))
+        while True:
+            b = rr_batch()
+            first = C.c_uint64()
+            self._ck(self.lib.dll.rr_collect_part(self.h, C.byref(b), C.byref(first)))
+            if b.n_reads == 0:
+                return
+            yield int(first.value), Batch(b)
+
     def kernel_launches(self):
         return int(self.lib.dll.rr_kernel_launches(self.h))
 
@@ -266,6 +281,9 @@ class Context:
         bad = C.c_uint64()
         self._ck(self.lib.dll.rr_debug_div_check(self.h, seed, n, C.byref(bad)))
         return bad.value
+
+    def debug_set_part_bytes(self, nbytes):
+        self._ck(self.lib.dll.rr_debug_set_part_bytes(self.h, nbytes))
 
     def debug_set_slack(self, slack=0.0):
         n = C.c_uint64()

@@ -97,6 +97,18 @@ struct rr_ctx {
   };
   Slot slot[2];
   uint64_t n_submitted = 0, n_collected = 0;
+  // streaming drain (rr_collect_begin / rr_collect_part): a ring of small pinned buffers instead of whole-batch staging
+  struct Part {
+    PinBuf seq, qual;
+    std::vector<uint64_t> off;  // record offsets relative to the part
+    cudaEvent_t ev = nullptr;
+    uint64_t first = 0, last = 0;
+  };
+  static constexpr int N_PARTS = 3;
+  uint64_t part_bytes = 32ull << 20;  // rr_debug_set_part_bytes
+  Part part[N_PARTS];
+  bool draining = false;
+  uint64_t drain_queued = 0, drain_returned = 0, drain_next_read = 0;  // parts queued / handed out; first read not yet queued
   int last_slot = 0;  // slot of the most recently completed run (debug fetch, timings)
   cudaStream_t copy_stream = nullptr;
   double initial_slack = 1.5;  // capacity planning slack (rr_debug_set_slack)
@@ -194,6 +206,11 @@ RR_API void rr_destroy(rr_ctx* ctx) {
     for (auto* b : pins) b->release();
     for (auto& ev : sl.ev) if (ev) cudaEventDestroy(ev);
     if (sl.done) cudaEventDestroy(sl.done);
+  }
+  for (auto& pt : ctx->part) {
+    pt.seq.release();
+    pt.qual.release();
+    if (pt.ev) cudaEventDestroy(pt.ev);
   }
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
   if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
@@ -810,6 +827,7 @@ RR_API int rr_submit(rr_ctx* ctx, uint64_t n, const rr_desc* descs) {
 RR_API int rr_collect(rr_ctx* ctx, rr_batch* out) {
   if (!ctx || !out) return RR_ERR_ARG;
   if (ctx->n_submitted == ctx->n_collected) return fail(ctx, RR_ERR_ARG, "rr_collect: nothing submitted");
+  if (ctx->draining) return fail(ctx, RR_ERR_ARG, "rr_collect: a batch is being drained with rr_collect_part");
   CK(cudaSetDevice(ctx->device));
   Slot& sl = ctx->slot[ctx->n_collected & 1];
   ctx->n_collected += 1;
@@ -820,6 +838,96 @@ RR_API int rr_collect(rr_ctx* ctx, rr_batch* out) {
   rc = fetch(ctx, sl, out);
   trace("collect: D2H done", ctx->n_collected - 1);
   return rc;
+}
+
+// ---- streaming drain -----------------------------------------------------------------------------------------------------
+// queue the D2H of the next part of the draining batch into ring slot (drain_queued % N_PARTS)
+static int queue_part(rr_ctx* ctx, Slot& sl) {
+  const uint64_t* off = sl.h_off.as<uint64_t>();
+  const uint64_t first = ctx->drain_next_read;
+  uint64_t last = first + 1;
+  while (last < sl.n && off[last + 1] - off[first] <= ctx->part_bytes) ++last;
+  rr_ctx::Part& pt = ctx->part[ctx->drain_queued % rr_ctx::N_PARTS];
+  const uint64_t bytes = off[last] - off[first];
+  ENSURE(pt.seq, std::max<uint64_t>(bytes, ctx->part_bytes) + 16);
+  ENSURE(pt.qual, std::max<uint64_t>(bytes, ctx->part_bytes) + 16);
+  if (!pt.ev) CK(cudaEventCreateWithFlags(&pt.ev, cudaEventDisableTiming));
+  if (bytes) {
+    CK(cudaMemcpyAsync(pt.seq.p, sl.d_seq.as<uint8_t>() + off[first], bytes, cudaMemcpyDeviceToHost, ctx->copy_stream));
+    CK(cudaMemcpyAsync(pt.qual.p, sl.d_qual.as<uint8_t>() + off[first], bytes, cudaMemcpyDeviceToHost, ctx->copy_stream));
+  }
+  CK(cudaEventRecord(pt.ev, ctx->copy_stream));
+  pt.first = first;
+  pt.last = last;
+  pt.off.resize(last - first + 1);
+  for (uint64_t i = first; i <= last; ++i) pt.off[i - first] = off[i] - off[first];
+  ctx->drain_next_read = last;
+  ctx->drain_queued += 1;
+  return RR_OK;
+}
+
+RR_API int rr_collect_begin(rr_ctx* ctx, uint64_t* n_reads, uint64_t* total_bases) {
+  if (!ctx) return RR_ERR_ARG;
+  if (ctx->n_submitted == ctx->n_collected) return fail(ctx, RR_ERR_ARG, "rr_collect_begin: nothing submitted");
+  if (ctx->draining) return fail(ctx, RR_ERR_ARG, "rr_collect_begin: the previous batch is still being drained (call rr_collect_part until it returns no reads)");
+  CK(cudaSetDevice(ctx->device));
+  Slot& sl = ctx->slot[ctx->n_collected & 1];
+  int rc = finish(ctx, sl);
+  if (rc) { ctx->n_collected += 1; return rc; }
+  const uint64_t n = sl.n;
+  ENSURE(sl.h_off, (n + 1) * 8);
+  ENSURE(sl.h_len, n * 8);
+  ENSURE(sl.h_id, n * 8);
+  cudaStream_t cs = ctx->copy_stream;
+  CK(cudaMemcpyAsync(sl.h_off.p, sl.d_packed_off.p, (n + 1) * 8, cudaMemcpyDeviceToHost, cs));
+  CK(cudaMemcpyAsync(sl.h_len.p, sl.d_err_len.p, n * 8, cudaMemcpyDeviceToHost, cs));
+  CK(cudaMemcpyAsync(sl.h_id.p, sl.d_real_id.p, n * 8, cudaMemcpyDeviceToHost, cs));
+  CK(cudaStreamSynchronize(cs));
+  ctx->draining = true;
+  ctx->drain_queued = ctx->drain_returned = 0;
+  ctx->drain_next_read = 0;
+  for (int i = 0; i < rr_ctx::N_PARTS && ctx->drain_next_read < n; ++i)
+    if ((rc = queue_part(ctx, sl))) return rc;
+  if (n_reads) *n_reads = n;
+  if (total_bases) *total_bases = sl.bases;
+  return RR_OK;
+}
+
+RR_API int rr_collect_part(rr_ctx* ctx, rr_batch* out, uint64_t* first) {
+  if (!ctx || !out) return RR_ERR_ARG;
+  if (!ctx->draining) return fail(ctx, RR_ERR_ARG, "rr_collect_part: no batch is being drained (rr_collect_begin first)");
+  CK(cudaSetDevice(ctx->device));
+  Slot& sl = ctx->slot[ctx->n_collected & 1];
+  // the part handed out by the previous call is finished with: its ring slot takes the next pending part
+  if (ctx->drain_returned > 0 && ctx->drain_next_read < sl.n) {
+    int rc = queue_part(ctx, sl);
+    if (rc) return rc;
+  }
+  std::memset(out, 0, sizeof *out);
+  out->k = ctx->M.k;
+  if (ctx->drain_returned == ctx->drain_queued) {  // everything handed out: the batch is collected
+    ctx->draining = false;
+    ctx->n_collected += 1;
+    if (first) *first = sl.n;
+    return RR_OK;
+  }
+  rr_ctx::Part& pt = ctx->part[ctx->drain_returned % rr_ctx::N_PARTS];
+  CK(cudaEventSynchronize(pt.ev));
+  ctx->drain_returned += 1;
+  const uint64_t* len = sl.h_len.as<uint64_t>();
+  uint64_t bases = 0;
+  for (uint64_t i = pt.first; i < pt.last; ++i)
+    if (len[i] > 14 && len[i] > 2ull * ctx->M.k) bases += len[i] - 2ull * ctx->M.k;  // writer: mod.rs:192-208
+  out->n_reads = pt.last - pt.first;
+  out->offsets = pt.off.data();
+  out->lengths = len + pt.first;
+  out->seq = pt.seq.as<uint8_t>();
+  out->qual = pt.qual.as<uint8_t>();
+  out->real_identity = sl.h_id.as<double>() + pt.first;
+  out->total_bytes = pt.off.back();
+  out->total_bases = bases;
+  if (first) *first = pt.first;
+  return RR_OK;
 }
 
 RR_API int rr_generate(rr_ctx* ctx, uint64_t n, const rr_desc* descs, rr_batch* out) {
@@ -931,6 +1039,13 @@ RR_API int rr_debug_div_check(rr_ctx* ctx, uint64_t seed, uint64_t n, uint64_t* 
   CK(cudaMemcpyAsync(mismatches, d.p, 8, cudaMemcpyDeviceToHost, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
   d.release();
+  return RR_OK;
+}
+
+RR_API int rr_debug_set_part_bytes(rr_ctx* ctx, uint64_t bytes) {
+  if (!ctx || bytes == 0) return RR_ERR_ARG;
+  if (ctx->draining) return fail(ctx, RR_ERR_ARG, "rr_debug_set_part_bytes: a batch is being drained");
+  ctx->part_bytes = bytes;
   return RR_OK;
 }
 

@@ -110,8 +110,16 @@ def _simulate_single_gpu(sim, total, limit, output, device, chunk_bases):
     """One GPU, pipelined: while chunk c is drained and written (writev from pinned memory), chunk c+1 is generated.
     Chunks are sub-ranges of ONE reference batch, so main_rng sees exactly the reference's order: all Fragments draws
     of the batch, then one u128 per emitted read in canonical order (src/simulate/mod.rs:163-203)."""
+    import os
+    import sys
+    import time
+
+    timing = os.environ.get("RUSTYREAD_B200_TIMING")  # developer aid: where the wall clock of a run goes (stderr)
+    acc = dict(context=0.0, feed=0.0, submit=0.0, collect=0.0, write=0.0)
+    t0 = time.perf_counter()
     ctx = capi.Context(device)
     sim.attach(ctx)
+    acc["context"] = time.perf_counter() - t0
     try:
         fd = output.fileno()
         output.flush()
@@ -121,24 +129,40 @@ def _simulate_single_gpu(sim, total, limit, output, device, chunk_bases):
     while produced < total:
         base_loop = min(limit, total - produced)
         produced += base_loop
+        t = time.perf_counter()
         descs = sim.feed(base_loop)
+        acc["feed"] += time.perf_counter() - t
         cb = chunk_bounds(descs, chunk_bases)
         nchunks = len(cb) - 1
         if nchunks <= 0:
             continue
+        t = time.perf_counter()
         ctx.submit(descs[cb[0]:cb[1]])
+        acc["submit"] += time.perf_counter() - t
         for c in range(nchunks):
             if c + 1 < nchunks:
+                t = time.perf_counter()
                 ctx.submit(descs[cb[c + 1]:cb[c + 2]])
-            b = ctx.collect()
-            if fd is not None:
-                recs, bases, _ = sim.write_fastq(b.struct, fd, first=cb[c])
-            else:
-                text, recs, bases = sim.fastq(b.struct, first=cb[c])
-                output.write(text)
-            n_reads += recs
-            n_bases += bases
+                acc["submit"] += time.perf_counter() - t
+            t = time.perf_counter()
+            for first, b in ctx.collect_parts():  # ~32 MiB parts through a small pinned ring; D2H of part p + 1 overlaps the write of part p
+                t1 = time.perf_counter()
+                acc["collect"] += t1 - t
+                if fd is not None:
+                    recs, bases, _ = sim.write_fastq(b.struct, fd, first=cb[c] + first)
+                else:
+                    text, recs, bases = sim.fastq(b.struct, first=cb[c] + first)
+                    output.write(text)
+                t = time.perf_counter()
+                acc["write"] += t - t1
+                n_reads += recs
+                n_bases += bases
+            acc["collect"] += time.perf_counter() - t
+    t = time.perf_counter()
     ctx.close()
+    acc["close"] = time.perf_counter() - t
+    if timing:
+        print("rustyread_b200 timing (s): " + ", ".join("%s %.3f" % kv for kv in acc.items()) + ", total %.3f" % (time.perf_counter() - t0), file=sys.stderr)
     return n_reads, n_bases
 
 

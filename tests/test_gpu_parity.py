@@ -453,6 +453,37 @@ def test_submit_collect_pipeline_matches_sync(orc):
     ctx.close()
 
 
+def test_streaming_drain_matches_whole_batch_collect(orc):
+    """rr_collect_begin / rr_collect_part hand over exactly what rr_collect does, part by part (many parts forced)."""
+    import rustyread_b200.capi as capi
+
+    fasta = helpers.random_fasta(orc, [150_000])
+    w, ctx, s = helpers.make_pair(orc, fasta, dict(length=(3000.0, 2500.0)))
+    w.feed(1_500_000)
+    d, ident, _ = w.items()
+    descs = capi.descs_from_oracle_items(d, ident)
+    whole = ctx.generate(descs)
+    want = [(bytes(whole.seq[int(o):int(o) + int(l)]), bytes(whole.qual[int(o):int(o) + int(l)]), float(i))
+            for o, l, i in zip(whole.offsets[:-1], whole.lengths, whole.real_identity)]
+    for part_bytes in (40_000, 7, 1 << 30):  # several reads per part; one read per part; one part
+        ctx.debug_set_part_bytes(part_bytes)
+        ctx.submit(descs)
+        ctx.submit(descs[: len(descs) // 2])  # a second batch in flight while the first is drained
+        got, nparts = [], 0
+        for first, b in ctx.collect_parts():
+            assert first == len(got)
+            nparts += 1
+            got += [(bytes(b.seq[int(o):int(o) + int(l)]), bytes(b.qual[int(o):int(o) + int(l)]), float(i))
+                    for o, l, i in zip(b.offsets[:-1], b.lengths, b.real_identity)]
+        assert got == want
+        assert nparts == (1 if part_bytes == 1 << 30 else nparts) and (part_bytes != 7 or nparts == len(descs))
+        second = ctx.collect()
+        assert second.n == len(descs) // 2 and np.array_equal(second.lengths, whole.lengths[: len(descs) // 2])
+    with pytest.raises(capi.RRError):
+        next(ctx.collect_parts())  # nothing submitted
+    ctx.close()
+
+
 def test_cli_simulate_matches_oracle(orc, tmp_path):
     """`python -m rustyread_b200 simulate` (the drop-in CLI) writes the same file as the oracle's simulate()."""
     import subprocess

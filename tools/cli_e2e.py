@@ -8,9 +8,9 @@ q = sys.argv[1] if len(sys.argv) > 1 else "1000x"
 for out in ("/dev/null", "/dev/shm/rr_reads.fastq"):
     t = time.time()
     r = subprocess.run([sys.executable, "-m", "rustyread_b200", "-v", "simulate", "--reference", ref, "--quantity", q, "--seed", "42", "--error_model", "random",
-                        "--qscore_model", "random", "--output", out], capture_output=True, text=True, cwd=os.path.join(os.path.dirname(__file__), ".."))
+                        "--qscore_model", "random", "--output", out], capture_output=True, text=True, env=dict(os.environ, RUSTYREAD_B200_TIMING="1"), cwd=os.path.join(os.path.dirname(__file__), ".."))
     dt = time.time() - t
-    print(out, "rc", r.returncode, r.stderr.strip()[-200:], "wall %.2fs" % dt)
+    print(out, "rc", r.returncode, r.stderr.strip()[-400:], "wall %.2fs" % dt)
     bases = int(r.stderr.strip().split()[-2]) if r.returncode == 0 else 0
     print("  -> %.2f Gbases/s whole process (incl. python start, reference parse, 100k length draws, context creation)" % (bases / dt / 1e9))
     if out != "/dev/null" and os.path.exists(out):
