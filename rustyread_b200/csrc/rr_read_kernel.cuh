@@ -568,16 +568,18 @@ __device__ __forceinline__ void process_read(const ReadKernelParams& P, WarpSmem
         if (replay) W.S.flags |= F_REPLAYED;  // remembered until the replayed event completes
       }
       const uint32_t pi = W.pos + (uint32_t)lane;
-      const bool inb = pi < W.L - k;
       const double rem = (double)(W.L - pi);
-      const bool brk = W.target < 0.0 || W.target > rem;
-      const bool gl = (pi == W.gbegin) && !(lane == 0 && (W.S.flags & F_GLITCH_CHECKED));
       const double p = walk_div(W.target, rem);
-      const bool one = (p == 1.0);
       const uint32_t wo = W.off + 2 * (uint32_t)lane;
       const uint64_t v = (uint64_t)ws->rng[wo] | ((uint64_t)ws->rng[wo + 1] << 32);
-      const bool hit = one || v < bernoulli_threshold(p);
-      const uint32_t m_any = __ballot_sync(0xffffffffu, !inb || gl || brk || hit);
+      // A position is `rare` when something other than a plain Bernoulli(p) draw with 0 <= p < 1 happens there: the end
+      // of the walk (pi == L - k), a glitch due, the break of error.rs:289-291 (target < 0 or target > rem, i.e. p > 1), or
+      // p == 1 (gen_bool draws nothing).  Only then are the flags of the winning lane needed.
+      const bool inb = pi < W.L - k;
+      const bool gl = (pi == W.gbegin) && !(lane == 0 && (W.S.flags & F_GLITCH_CHECKED));
+      const bool rare = !inb || gl || !(p < 1.0) || W.target < 0.0;
+      const uint32_t m_r = __ballot_sync(0xffffffffu, rare);
+      const uint32_t m_any = m_r | __ballot_sync(0xffffffffu, v < bernoulli_threshold(p));
       if (m_any == 0) {
         W.pos += 32;
         W.off += 64;
@@ -585,14 +587,23 @@ __device__ __forceinline__ void process_read(const ReadKernelParams& P, WarpSmem
         continue;
       }
       const int f = __ffs(m_any) - 1;
-      const uint32_t fl = (inb ? 1u : 0u) | (gl ? 2u : 0u) | (brk ? 4u : 0u) | (one ? 8u : 0u);
-      const uint32_t ff = __shfl_sync(0xffffffffu, fl, f);
       W.pos += (uint32_t)f;
       W.off += 2 * (uint32_t)f;
       if (f > 0) W.S.flags &= ~F_GLITCH_CHECKED;
-      if (!(ff & 1u)) break;  // pos == L - k
+      bool is_glitch = false;
+      uint32_t consume = 2;  // words of the Bernoulli draw
+      if ((m_r >> f) & 1u) {
+        const bool brk = W.target < 0.0 || W.target > rem;
+        const uint32_t fl = (inb ? 1u : 0u) | (gl ? 2u : 0u) | (brk ? 4u : 0u) | (p == 1.0 ? 8u : 0u);
+        const uint32_t ff = __shfl_sync(0xffffffffu, fl, f);
+        if (!(ff & 1u)) break;  // pos == L - k
+        is_glitch = (ff & 2u) != 0;
+        if (!is_glitch) {
+          if (ff & 4u) break;  // error.rs:289-291
+          if (ff & 8u) consume = 0;
+        }
+      }
       uint32_t edits;
-      const bool is_glitch = (ff & 2u) != 0;
       if (is_glitch) {  // glitch due at pos (error.rs:282-287)
         const uint32_t gwarp = blockIdx.x * WARPS_PER_BLOCK + (threadIdx.x >> 5);
         const GlitchRec* grec = P.sc_grec + (uint64_t)gwarp * P.sc_grec_cap;
@@ -605,9 +616,8 @@ __device__ __forceinline__ void process_read(const ReadKernelParams& P, WarpSmem
         walk_load(ws, W);
         W.S.flags |= F_GLITCH_CHECKED;  // same pos again, with the new target, glitch check done
       } else {
-        if (ff & 4u) break;  // error.rs:289-291
         const uint32_t off_ev = W.off;  // where a replay of this event starts
-        if (!(ff & 8u)) W.off += 2;
+        W.off += consume;
         // Error::add_errors_to_kmer (src/model/error.rs:93-107): the altered k-mer is built in registers, lane i = byte i
         const uint32_t kb = (uint32_t)lane < k ? (uint32_t)W.raw[W.pos + lane] : 0u;
         uint32_t c = 0, olen, fk, fep;
