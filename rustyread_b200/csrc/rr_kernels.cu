@@ -287,6 +287,7 @@ RR_API int rr_set_error_model(rr_ctx* ctx, uint32_t k, uint64_t n_keys, const ui
   if (k == 0 || k > 31) return fail(ctx, RR_ERR_UNSUPPORTED, "rr_set_error_model: k must be in 1..31");
   CK(cudaSetDevice(ctx->device));
   ctx->M.k = k;
+  ctx->M.em_alts_acgt = 1;
   if (n_keys == 0) {  // Error::random(k)
     ctx->M.em_index = nullptr;
     ctx->have_error = true;
@@ -316,6 +317,8 @@ RR_API int rr_set_error_model(rr_ctx* ctx, uint32_t k, uint64_t n_keys, const ui
   }
   std::vector<uint32_t> ab(alt_begin, alt_begin + n_keys + 1), ao(alt_off, alt_off + n_alts + 1);
   std::vector<uint8_t> bytes(alt_bytes, alt_bytes + alt_off[n_alts]);
+  for (uint8_t c : bytes)
+    if (!(c == 'A' || c == 'C' || c == 'G' || c == 'T')) ctx->M.em_alts_acgt = 0;
   // precomputed alignments: alternative j (of key i) against its key, for every piece offset es < len(alt), es <= k
   std::vector<uint32_t> piece_begin(n_alts + 1, 0), piece_off(1, 0);
   std::vector<uint8_t> piece_edits, piece_ops;

@@ -107,6 +107,30 @@ __device__ __forceinline__ uint64_t add_fragment(WarpRng& rng, const DeviceModel
   return n1 + n2;
 }
 
+// True when every byte of raw[0, L) is one of A, C, G, T (raw is 16-byte aligned).  Four bytes at a time: with
+// y = x ^ 0x41414141 the valid bytes are 0x00, 0x02, 0x06, 0x15, i.e. bits 3, 5, 6, 7 clear, bit 4 == bit 0, and
+// (bit 2 and not bit 1) == bit 0.
+__device__ __forceinline__ bool raw_is_acgt(const uint8_t* raw, uint32_t L, int lane) {
+  uint32_t bad = 0;
+  const uint4* v = reinterpret_cast<const uint4*>(raw);
+  for (uint32_t i = lane; i < L / 16; i += 32) {
+    const uint4 q = v[i];
+    const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const uint32_t y = w[j] ^ 0x41414141u;
+      const uint32_t b0 = y & 0x01010101u;
+      bad |= (y & 0xE8E8E8E8u) | (b0 ^ ((y >> 4) & 0x01010101u)) | (b0 ^ ((y >> 2) & ~(y >> 1) & 0x01010101u));
+    }
+  }
+  const uint32_t t = (L & ~15u) + (uint32_t)lane;  // fewer than 16 bytes left
+  if (t < L) {
+    const uint8_t c = raw[t];
+    bad |= !(c == 'A' || c == 'C' || c == 'G' || c == 'T');
+  }
+  return !__any_sync(0xffffffffu, bad != 0);
+}
+
 // ---- K2 (out of line): the raw fragment of generate_read, src/simulate/mod.rs:243-271.  value = raw length ----
 __device__ __noinline__ StageOut stage_assemble(uint32_t ws32, uint32_t off, int lane, const ReadKernelParams& P, uint32_t ridx, uint8_t* raw) {
   const DeviceModels& M = P.M;
@@ -131,7 +155,7 @@ __device__ __noinline__ StageOut stage_assemble(uint32_t ws32, uint32_t off, int
   StageOut o;
   o.off = rng.off;
   o.value = L;
-  o.status = ST_OK;
+  o.status = raw_is_acgt(raw, (uint32_t)L, lane) ? 0u : 1u;  // 1: some byte outside ACGT (alignments must check their windows)
   return o;
 }
 
@@ -183,9 +207,9 @@ struct Stitch {
   uint32_t pos_in_raw;   // sequence(): end of the last emitted change
   uint32_t real_edit;
   uint32_t le, lee, ledit;
-  uint32_t flags;        // F_HAS_LAST | F_EMIT | F_GLITCH_CHECKED | F_REPLAY | F_REPLAYED | status << 8
+  uint32_t flags;        // F_HAS_LAST | F_EMIT | F_GLITCH_CHECKED | F_REPLAY | F_REPLAYED | F_DIRTY (bytes outside ACGT around) | status << 8
 };
-enum : uint32_t { F_HAS_LAST = 1u, F_EMIT = 2u, F_GLITCH_CHECKED = 4u, F_REPLAY = 8u, F_REPLAYED = 16u, F_STATUS_SHIFT = 8u };
+enum : uint32_t { F_HAS_LAST = 1u, F_EMIT = 2u, F_GLITCH_CHECKED = 4u, F_REPLAY = 8u, F_REPLAYED = 16u, F_DIRTY = 32u, F_STATUS_SHIFT = 8u };
 
 // Everything the error walk carries from one position to the next.  The walk keeps it in registers; around EVERY
 // out-of-line call inside the loop it is parked in WarpSmem::st and read back, so that no value is live across a call:
@@ -491,7 +515,7 @@ __device__ __forceinline__ uint32_t add_change_reg(Walk& W, WarpSmem* ws, const 
         if (add + tn <= 16u && add != 0 && tn != 0) {
           const uint32_t qc = __shfl_sync(0xffffffffu, c, (lane - 1 + (int)es) & 31);
           const uint32_t tc = (uint32_t)lane < tn ? W.raw[cp.rs + lane] : (uint32_t)'A';
-          a = warp_align_small(qc, add, tc, tn, emit ? ws->cigb : nullptr, S.cig_len, lane);
+          a = warp_align_small(qc, add, tc, tn, emit ? ws->cigb : nullptr, S.cig_len, (S.flags & F_DIRTY) != 0, lane);
         }
         if (a == ~0ULL) cold = true;  // more than 16 ops or a byte outside ACGT
         else {
@@ -528,6 +552,7 @@ __device__ __forceinline__ void process_read(const ReadKernelParams& P, WarpSmem
     W.off = so.off;
     W.L = (uint32_t)so.value;
     W.raw = raw;
+    W.S.flags = (so.status || !M.em_alts_acgt) ? F_DIRTY : 0u;
   }
   W.ridx = ridx;
   W.pos = 0;
@@ -535,7 +560,6 @@ __device__ __forceinline__ void process_read(const ReadKernelParams& P, WarpSmem
   W.S.err_len = W.S.cig_len = 0;
   W.S.pos_in_raw = 0;
   W.S.real_edit = 0;
-  W.S.flags = 0;
   W.S.le = W.S.lee = W.S.ledit = 0;
   __syncwarp();
   ws->st[ST_CAP] = (uint32_t)(P.out_off[ridx + 1] - P.out_off[ridx]);
