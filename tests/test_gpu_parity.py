@@ -184,6 +184,24 @@ def test_config1_default(orc):
     ctx.close()
 
 
+def test_config2_full_size_5mbp_200x(orc):
+    """BASELINE.json configs[1] at its full size (the bench workload): 5 Mbp reference, 200x, seed 42, defaults —
+    every byte of all ~66 000 reads (1.0 Gbases) against the oracle, which needs ~10 s on the box's host threads."""
+    import os
+
+    import rustyread_b200.capi as capi
+
+    fasta = helpers.random_fasta(orc, [5_000_000])
+    w, ctx, s = helpers.make_pair(orc, fasta, {})
+    n = w.feed(1_000_000_000)
+    d, ident, _ = w.items()
+    batch = ctx.generate(capi.descs_from_oracle_items(d, ident))
+    w.generate(threads=os.cpu_count() or 8, keep_cigar_raw=False)
+    helpers.compare_batch(w, batch, None, check_intermediate=False)
+    assert n > 60_000 and batch.total_bases > 990_000_000
+    ctx.close()
+
+
 def test_config4_ultralong_low_identity(orc):
     fasta = helpers.random_fasta(orc, [600_000])
     spec = dict(length=(50000.0, 40000.0), identity=(75.0, 90.0, 8.0), glitch=(2000.0, 50.0, 50.0), rates=(1.0, 1.0, 5.0))
