@@ -1,7 +1,6 @@
 """`python -m rustyread_b200 simulate ...` — the `rustyread simulate` command line (src/cli/mod.rs:10-28,
 src/cli/simulate.rs:162-239) over the B200 library.  Under torchrun every rank drives its own GPU."""
 import argparse
-import gzip
 import os
 import sys
 
@@ -35,8 +34,7 @@ def main(argv=None):
         import torch.distributed as dist
 
         dist.init_process_group("gloo")  # shard results travel host to host; the data path itself has no collective
-    raw = open(a.reference, "rb").read()
-    fasta = gzip.decompress(raw) if raw[:2] == b"\x1f\x8b" else raw
+    fasta = sim_mod.read_maybe_compressed(a.reference)  # niffler: plain, gz, bz2 or xz by magic number
     out = (open(a.output, "wb") if a.output else sys.stdout.buffer) if rank == 0 else None
     flags = {k: getattr(a, k) for k in d}
     chunk = int(os.environ.get("RUSTYREAD_B200_CHUNK_BASES", "1000000000"))  # device chunk size inside one reference batch

@@ -21,6 +21,25 @@ FLAG_DEFAULTS = dict(  # src/cli/simulate.rs:165-238
 )
 
 
+def read_maybe_compressed(path):
+    """Whole file, decompressed by magic number like niffler::get_reader does for the reference and the model files
+    (src/simulate/mod.rs:46,96,121; Cargo.toml:38 enables gz, bz2 and lzma/xz)."""
+    raw = open(path, "rb").read()
+    if raw[:2] == b"\x1f\x8b":
+        import gzip
+
+        return gzip.decompress(raw)
+    if raw[:3] == b"BZh":
+        import bz2
+
+        return bz2.decompress(raw)
+    if raw[:6] == b"\xfd7zXZ\x00":
+        import lzma
+
+        return lzma.decompress(raw)
+    return raw
+
+
 def parse_duo(text):  # cli::simulate::Duo, src/cli/simulate.rs:82-101
     parts = text.split(",")
     if len(parts) != 2 or not all(p.isdigit() for p in parts):
@@ -180,12 +199,7 @@ def simulate(fasta, quantity, output, generate_factory=None, dist=None, rank=0, 
                                     "pass a model file, 'random' or (qscore) 'ideal'")
 
     def model_text(v, builtins):
-        if v in builtins:
-            return v
-        import gzip
-
-        raw = open(v, "rb").read()
-        return gzip.decompress(raw) if raw[:2] == b"\x1f\x8b" else raw
+        return v if v in builtins else read_maybe_compressed(v)
 
     sim = capi.Simulation(fasta, seed=f["seed"], length=parse_duo(f["length"]), identity=parse_trio(f["identity"]),
                           start_adapter=parse_duo(f["start_adapter"]), end_adapter=parse_duo(f["end_adapter"]),

@@ -82,6 +82,21 @@ def test_flag_parsers():
         parse_trio("1,2")
 
 
+def test_compressed_inputs_are_sniffed_like_niffler(tmp_path):
+    """Reference and model files may be plain, gz, bz2 or xz (niffler, src/simulate/mod.rs:46,96,121; Cargo.toml:38)."""
+    import bz2
+    import gzip
+    import lzma
+
+    from rustyread_b200.simulate import read_maybe_compressed
+
+    text = b">c\nACGTACGT\n" * 50
+    for name, data in (("plain", text), ("gz", gzip.compress(text)), ("bz2", bz2.compress(text)), ("xz", lzma.compress(text))):
+        p = tmp_path / ("ref." + name)
+        p.write_bytes(data)
+        assert read_maybe_compressed(str(p)) == text
+
+
 def test_world_size_2_simulate_matches_single_process(orc, tmp_path):
     fasta = helpers.random_fasta(orc, [70_000, 5_000], circular={1})
     fpath, opath, wpath = tmp_path / "ref.fa", tmp_path / "out.fq", tmp_path / "worker.py"

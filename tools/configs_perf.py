@@ -38,7 +38,11 @@ CASES = [
     ("ref5m 200x random error model, ideal qscores", ref5m, dict(qscore_model="ideal"), 5_000_000 * 200),
 ]
 out = []
+only = os.environ.get("RR_CASES")  # comma separated indices
+if only:
+    CASES = [CASES[int(i)] for i in only.split(",")]
 for name, fasta, spec, target in CASES:
+    t_case = time.time()
     w, ctx, s = helpers.make_pair(orc, fasta, spec)
     n = w.feed(int(target))
     d, ident, _ = w.items()
@@ -53,7 +57,10 @@ for name, fasta, spec, target in CASES:
     bases = ctx.last_run_bases()
     e2e = float("nan")
     if "resident only" not in name:
-        ctx.generate(descs)
+        ctx.submit(descs)  # warm both batch slots (their pinned staging is allocated on first use)
+        ctx.submit(descs)
+        ctx.collect()
+        ctx.collect()
         t = time.perf_counter()
         reps = 3
         ctx.submit(descs)
@@ -64,6 +71,7 @@ for name, fasta, spec, target in CASES:
         e2e = reps * bases / (time.perf_counter() - t)
     line = {"case": name, "reads": int(n), "bases": int(bases), "kernels_ms": best, "resident_gbases_per_s": bases / best["total"] / 1e6,
             "host_to_host_gbases_per_s": (e2e / 1e9) if e2e == e2e else None}
+    line["case_wall_s"] = time.time() - t_case
     print(json.dumps(line), flush=True)
     out.append(line)
     ctx.close()
