@@ -56,12 +56,12 @@ def measured_peak():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-def ncu_traffic():
-    """dram bytes per launch of the dominant kernel, from the committed ncu summary (None if absent)."""
+def ncu_traffic(key="dram_bytes_per_launch"):
+    """dram bytes (or warp instructions) per launch of the dominant kernel, from the committed ncu summary (None if absent)."""
     p = os.path.join(ROOT, "profiles", "read_kernel_traffic.json")
     if os.path.exists(p):
         try:
-            return json.load(open(p)).get("dram_bytes_per_launch")
+            return json.load(open(p)).get(key)
         except Exception:
             return None
     return None
@@ -165,7 +165,7 @@ def run_reference_arm(args, rank):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--coverage", type=int, default=COVERAGE, help=argparse.SUPPRESS)
@@ -298,6 +298,14 @@ def main():
                          "algorithmic_bytes_per_launch": ALG_BYTES_PER_BASE * per_launch_bases, "kernel_ms": read_ms / args.steps,
                          "kernel_share_of_step": read_ms / dev_ms if dev_ms else None,
                          "note": "3 B/base (SURVEY §8d); the kernel is bound by integer issue on a serial RNG/alignment chain, not by HBM"},
+            # what actually bounds the kernel: warp instructions issued (ncu count of the committed profile of this same
+            # workload) over the live kernel time, against one instruction per scheduler per clock at the sampled SM clock
+            "issue_rate": (lambda wi, mhz: None if not wi or not mhz else {
+                "warp_instructions_per_launch": wi, "achieved_ginst_per_s": wi / read_kernel_s / 1e9,
+                "peak_ginst_per_s": torch.cuda.get_device_properties(local_rank).multi_processor_count * 4 * mhz / 1e3,
+                "frac": wi / read_kernel_s / (torch.cuda.get_device_properties(local_rank).multi_processor_count * 4 * mhz * 1e6),
+                "source": "smsp__inst_executed.sum from profiles/read_kernel_traffic.json; peak = SMs x 4 schedulers x sm_mhz"})(
+                ncu_traffic("warp_instructions_per_launch"), clocks.get("sm_mhz")),
             "kernels_ms_per_step": {"rr_read_kernel": read_ms / args.steps, "rr_qscore_kernel(+scan)": q_ms / args.steps, "rr_pack_kernel": pack_ms / args.steps},
         }
         if world == 1 and not args.no_cpu_baseline:

@@ -19,6 +19,7 @@ if len(sys.argv) > 3:
     json.dump({"kernel": "rr_read_kernel", "workload": "bench.py default (ref5m 200x)",
                "dram_bytes_per_launch": out[k]["dram_read_bytes_per_launch"] + out[k]["dram_write_bytes_per_launch"],
                "dram_read_bytes_per_launch": out[k]["dram_read_bytes_per_launch"], "dram_write_bytes_per_launch": out[k]["dram_write_bytes_per_launch"],
+               "warp_instructions_per_launch": out[k]["warp_instructions_per_launch"],
                "source": "ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum,... --clock-control none (%s)" % sys.argv[1]},
               open(sys.argv[3], "w"), indent=1)
 print(json.dumps(out, indent=1)[:1500])
