@@ -145,6 +145,10 @@ int rr_collect(rr_ctx* ctx, rr_batch* out);
  *                     counts as collected. */
 int rr_collect_begin(rr_ctx* ctx, uint64_t* n_reads, uint64_t* total_bases);
 int rr_collect_part(rr_ctx* ctx, rr_batch* part, uint64_t* first);
+/* Between rr_collect_begin and the last rr_collect_part: the lengths and identities (mod.rs:289-290) of ALL reads of the
+ * draining batch, library-owned.  A writer that shares its output file with other processes sizes its records from these
+ * before the first part arrives (rr_sim_fastq_bytes). */
+int rr_collect_meta(rr_ctx* ctx, const uint64_t** lengths, const double** real_identity);
 
 /* number of kernel launches issued by this context so far, and device milliseconds spent in the
  * last rr_run (CUDA events on the context's stream): [0] whole run, [1] read kernel (assemble +

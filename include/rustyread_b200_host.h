@@ -72,6 +72,12 @@ int rr_sim_fastq(rr_sim* s, const rr_batch* batch, uint64_t first, const char** 
 int rr_sim_write_fastq(rr_sim* s, const rr_batch* batch, uint64_t first, int fd, uint64_t* n_records, uint64_t* n_bases,
                        uint64_t* n_bytes);
 
+/* Bytes, records and bases of the text rr_sim_fastq / rr_sim_write_fastq produce for items [first, first + n) of the last
+ * feed, given their final lengths and identities; formats the comments only and draws nothing from main_rng (a read
+ * name is always 36 characters).  Lets several writers place their records in one file without a gather. */
+int rr_sim_fastq_bytes(rr_sim* s, uint64_t n, const uint64_t* lengths, const double* real_identity, uint32_t k, uint64_t first,
+                       uint64_t* n_bytes, uint64_t* n_records, uint64_t* n_bases);
+
 /* Advance main_rng past the read-name draws of `n_records` emitted reads (2 u64 each, mod.rs:201) without
  * formatting anything: what the ranks that do not write the file call to stay in step with the writer rank. */
 int rr_sim_skip_names(rr_sim* s, uint64_t n_records);

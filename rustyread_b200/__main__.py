@@ -25,6 +25,9 @@ def main(argv=None):
     s.add_argument("--small_plasmid_bias", action="store_true")
     s.add_argument("--number_base_store", default=None)
     a = ap.parse_args(argv)
+    import time
+
+    t_start = time.perf_counter()
 
     rank, world, local = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("LOCAL_RANK", "0"))
     from .placement import bind_to_gpu_numa
@@ -38,9 +41,13 @@ def main(argv=None):
     out = (open(a.output, "wb") if a.output else sys.stdout.buffer) if rank == 0 else None
     flags = {k: getattr(a, k) for k in d}
     chunk = int(os.environ.get("RUSTYREAD_B200_CHUNK_BASES", "1000000000"))  # device chunk size inside one reference batch
-    reads, bases = sim_mod.simulate(fasta, a.quantity, out, dist=dist, rank=rank, world=world, device=local, chunk_bases=chunk, **flags)
+    # several ranks + a regular output file: every rank writes its own records in place (RUSTYREAD_B200_SINGLE_WRITER=1: gather on rank 0)
+    par = a.output if (world > 1 and a.output and not os.environ.get("RUSTYREAD_B200_SINGLE_WRITER")) else None
+    reads, bases = sim_mod.simulate(fasta, a.quantity, out, dist=dist, rank=rank, world=world, device=local, chunk_bases=chunk, output_path=par, **flags)
     if rank == 0 and a.verbosity:
         print("wrote %d reads, %d bases" % (reads, bases), file=sys.stderr)
+    if os.environ.get("RUSTYREAD_B200_TIMING"):
+        print("rustyread_b200 timing rank %d: main() %.3f s" % (rank, time.perf_counter() - t_start), file=sys.stderr)
     if dist is not None:
         dist.destroy_process_group()
     return 0

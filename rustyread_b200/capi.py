@@ -52,6 +52,7 @@ EXPORTS = {
     "rr_collect": (C.c_int, [C.c_void_p, C.POINTER(rr_batch)]),
     "rr_collect_begin": (C.c_int, [C.c_void_p, u64p, u64p]),
     "rr_collect_part": (C.c_int, [C.c_void_p, C.POINTER(rr_batch), u64p]),
+    "rr_collect_meta": (C.c_int, [C.c_void_p, C.POINTER(u64p), C.POINTER(f64p)]),
     "rr_kernel_launches": (C.c_uint64, [C.c_void_p]),
     "rr_last_run_ms": (C.c_int, [C.c_void_p, C.POINTER(C.c_float)]),
     "rr_last_run_bases": (C.c_uint64, [C.c_void_p]),
@@ -241,6 +242,28 @@ class Context:
         self._ck(self.lib.dll.rr_collect(self.h, C.byref(b)))
         return Batch(b)
 
+    def collect_begin(self):
+        """Wait for the oldest submitted batch; returns (n_reads, total_bases, lengths, real_identity) — the two arrays are
+        copies of the whole batch's metadata (rr_collect_meta).  Follow with parts()."""
+        n, bases = C.c_uint64(), C.c_uint64()
+        self._ck(self.lib.dll.rr_collect_begin(self.h, C.byref(n), C.byref(bases)))
+        lp, ip = u64p(), f64p()
+        self._ck(self.lib.dll.rr_collect_meta(self.h, C.byref(lp), C.byref(ip)))
+        nn = int(n.value)
+        lengths = np.ctypeslib.as_array(lp, shape=(nn,)).copy() if nn else np.zeros(0, np.uint64)
+        ident = np.ctypeslib.as_array(ip, shape=(nn,)).copy() if nn else np.zeros(0, np.float64)
+        return nn, int(bases.value), lengths, ident
+
+    def parts(self):
+        """After collect_begin(): yields (first_read, Batch) for consecutive parts of the draining batch."""
+        while True:
+            b = rr_batch()
+            first = C.c_uint64()
+            self._ck(self.lib.dll.rr_collect_part(self.h, C.byref(b), C.byref(first)))
+            if b.n_reads == 0:
+                return
+            yield int(first.value), Batch(b)
+
     def collect_parts(self):
         """Streaming form of collect(): yields (first_read, Batch) for consecutive parts of the oldest submitted batch."""
         n, bases = C.c_uint64(), C.c_uint64()
@@ -354,6 +377,7 @@ HOST_EXPORTS = {
     "rr_sim_fastq": (C.c_int, [C.c_void_p, C.POINTER(rr_batch), C.c_uint64, C.POINTER(C.c_void_p), u64p, u64p, u64p]),
     "rr_sim_write_fastq": (C.c_int, [C.c_void_p, C.POINTER(rr_batch), C.c_uint64, C.c_int, u64p, u64p, u64p]),
     "rr_sim_skip_names": (C.c_int, [C.c_void_p, C.c_uint64]),
+    "rr_sim_fastq_bytes": (C.c_int, [C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint64, u64p, u64p, u64p]),
     "rr_sim_item_description": (C.c_int, [C.c_void_p, C.c_uint64, C.c_char_p, C.c_uint64]),
     "rr_sim_n_refs": (C.c_uint64, [C.c_void_p]),
     "rr_sim_ref": (C.c_void_p, [C.c_void_p, C.c_uint64, u64p, C.POINTER(C.c_int), f64p, C.POINTER(C.c_char_p)]),
@@ -445,6 +469,15 @@ class Simulation:
         recs, bases, nbytes = C.c_uint64(), C.c_uint64(), C.c_uint64()
         self._ck(self.lib.dll.rr_sim_write_fastq(self.h, C.byref(batch_struct), first, fd, C.byref(recs), C.byref(bases), C.byref(nbytes)))
         return recs.value, bases.value, nbytes.value
+
+    def fastq_bytes(self, lengths, real_identity, first=0):
+        """(bytes, records, bases) of the FASTQ text for items [first, first + n) with these final lengths / identities."""
+        lengths = np.ascontiguousarray(lengths, np.uint64)
+        real_identity = np.ascontiguousarray(real_identity, np.float64)
+        nb, nr, nbs = C.c_uint64(), C.c_uint64(), C.c_uint64()
+        self._ck(self.lib.dll.rr_sim_fastq_bytes(self.h, len(lengths), lengths.ctypes.data, real_identity.ctypes.data, self.k, first,
+                                                 C.byref(nb), C.byref(nr), C.byref(nbs)))
+        return int(nb.value), int(nr.value), int(nbs.value)
 
     def skip_names(self, n_records):
         self._ck(self.lib.dll.rr_sim_skip_names(self.h, n_records))

@@ -786,6 +786,29 @@ RR_API int rr_sim_write_fastq(rr_sim* s, const rr_batch* b, uint64_t first, int 
   return RR_OK;
 }
 
+RR_API int rr_sim_fastq_bytes(rr_sim* s, uint64_t n, const uint64_t* lengths, const double* real_identity, uint32_t k, uint64_t first,
+                              uint64_t* n_bytes, uint64_t* n_records, uint64_t* n_bases) {
+  if (!s || (n && (!lengths || !real_identity))) return RR_ERR_ARG;
+  if (first + n > s->items.size()) return sfail(s, RR_ERR_ARG, "rr_sim_fastq_bytes: range does not match the last feed");
+  uint64_t bytes = 0, recs = 0, bases = 0;
+  std::string comment;
+  for (uint64_t i = 0; i < n; ++i) {
+    const uint64_t l = lengths[i];
+    if (l <= 14) continue;  // mod.rs:192-194
+    if (l < 2ULL * k) return sfail(s, RR_ERR_READ, "rr_sim_fastq_bytes: read shorter than 2k (the reference panics slicing it)");
+    comment.clear();
+    append_description(s, comment, s->items[first + i], l, real_identity[i]);
+    const uint64_t nb = l - 2ULL * k;
+    bytes += 1 + 36 + 1 + comment.size() + 1 + nb + 3 + comment.size() + 1 + nb + 1;  // "@uuid comment\n" seq "\n+ comment\n" qual "\n"
+    ++recs;
+    bases += nb;
+  }
+  if (n_bytes) *n_bytes = bytes;
+  if (n_records) *n_records = recs;
+  if (n_bases) *n_bases = bases;
+  return RR_OK;
+}
+
 RR_API int rr_sim_skip_names(rr_sim* s, uint64_t n_records) {
   if (!s) return RR_ERR_ARG;
   for (uint64_t i = 0; i < 2 * n_records; ++i) s->rng.next_u64();

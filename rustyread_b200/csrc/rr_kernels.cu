@@ -896,6 +896,15 @@ RR_API int rr_collect_begin(rr_ctx* ctx, uint64_t* n_reads, uint64_t* total_base
   return RR_OK;
 }
 
+RR_API int rr_collect_meta(rr_ctx* ctx, const uint64_t** lengths, const double** real_identity) {
+  if (!ctx) return RR_ERR_ARG;
+  if (!ctx->draining) return fail(ctx, RR_ERR_ARG, "rr_collect_meta: no batch is being drained (rr_collect_begin first)");
+  const Slot& sl = ctx->slot[ctx->n_collected & 1];
+  if (lengths) *lengths = sl.h_len.as<uint64_t>();
+  if (real_identity) *real_identity = sl.h_id.as<double>();
+  return RR_OK;
+}
+
 RR_API int rr_collect_part(rr_ctx* ctx, rr_batch* out, uint64_t* first) {
   if (!ctx || !out) return RR_ERR_ARG;
   if (!ctx->draining) return fail(ctx, RR_ERR_ARG, "rr_collect_part: no batch is being drained (rr_collect_begin first)");

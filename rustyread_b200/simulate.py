@@ -80,6 +80,10 @@ class DeviceGenerator:
         self.ctx = capi.Context(device)
         sim.attach(self.ctx)
 
+    def batch(self, descs):
+        """The library-owned batch (pinned arenas, valid until the next call); None for an empty shard."""
+        return self.ctx.generate(descs) if len(descs) else None
+
     def __call__(self, descs):
         if len(descs) == 0:
             return (np.zeros(1, np.uint64), np.zeros(0, np.uint64), np.zeros(0, np.uint8), np.zeros(0, np.uint8), np.zeros(0, np.float64))
@@ -111,6 +115,92 @@ def _recv(dist, dtypes, src):
             dist.recv(t, src)
         out.append(t.numpy().view(dt))
     return out
+
+
+def piece_bounds(descs, world, chunk_bases):
+    """Split a reference batch into rounds x world contiguous pieces of about the same number of bases, each at most
+    ~chunk_bases: in round j rank r takes piece j * world + r, so the file order (= canonical read order) is round-major
+    and the offsets of a round are known as soon as the sizes of that round are."""
+    n = len(descs)
+    w = np.where(descs["type"] == capi.RR_REAL, np.abs(descs["end"].astype(np.int64) - descs["start"].astype(np.int64)), descs["end"].astype(np.int64))
+    cw = np.abs(descs["cend"].astype(np.int64) - descs["cstart"].astype(np.int64))
+    w = w + np.where(descs["has_chimera"] == 1, cw, 0) + 64
+    csum = np.cumsum(w) if n else np.zeros(1, np.int64)
+    total = int(csum[-1]) if n else 0
+    rounds = max(1, -(-total // max(1, world * chunk_bases)))
+    pieces = rounds * world
+    bounds = [0] + [int(np.searchsorted(csum, total * i / pieces)) for i in range(1, pieces)] + [n]
+    for i in range(1, len(bounds)):
+        bounds[i] = min(n, max(bounds[i], bounds[i - 1]))
+    return rounds, bounds
+
+
+def _write_batch_in_place(sim, gen, descs, dist, rank, world, pw, chunk_bases):
+    """Parallel writer of one reference batch: in every round this rank generates one piece, formats its records and
+    writes them at their final byte offset of the shared output file.  Read names are drawn from main_rng in write
+    order (src/simulate/mod.rs:199-203), so a rank first learns how many records the pieces before its own emit (reads
+    of 14 bases or fewer are dropped, mod.rs:192-194), skips that many name draws, draws its own, and skips the rest:
+    all main_rng copies leave the round in the same state.  One tiny all_gather per round, no data-path collective.
+    On the device path the next round's piece is generated while this one is drained in ~32 MiB parts and written with
+    writev straight from pinned memory."""
+    import os
+    import time
+
+    import torch
+
+    acc = pw.setdefault("acc", dict(generate=0.0, exchange=0.0, write=0.0))
+    rounds, pb = piece_bounds(descs, world, chunk_bases)
+    device = hasattr(gen, "ctx")
+    mine = [(pb[j * world + rank], pb[j * world + rank + 1]) for j in range(rounds)]
+    if device and mine[0][1] > mine[0][0]:
+        gen.ctx.submit(descs[mine[0][0]:mine[0][1]])
+    tot_reads = tot_bases = 0
+    for j, (lo, hi) in enumerate(mine):
+        t0 = time.perf_counter()
+        if device and j + 1 < rounds and mine[j + 1][1] > mine[j + 1][0]:
+            gen.ctx.submit(descs[mine[j + 1][0]:mine[j + 1][1]])  # generated while this round is drained
+        b = None
+        nbytes = recs = bases = 0
+        if hi > lo:
+            if device:
+                _, _, lens, ident = gen.ctx.collect_begin()
+            else:
+                off, lens, seq, qual, ident = gen(descs[lo:hi])
+                b = capi.batch_struct_from_arrays(off, lens, seq if len(seq) else np.zeros(1, np.uint8), qual if len(qual) else np.zeros(1, np.uint8), ident, sim.k)
+            nbytes, recs, bases = sim.fastq_bytes(lens, ident, first=lo)
+        t1 = time.perf_counter()
+        t = torch.tensor([recs, nbytes, bases], dtype=torch.int64)
+        got = [torch.zeros_like(t) for _ in range(world)]
+        dist.all_gather(got, t)
+        got = [[int(x) for x in g.tolist()] for g in got]
+        sim.skip_names(sum(g[0] for g in got[:rank]))
+        t2 = time.perf_counter()
+        pos = pw["pos"] + sum(g[1] for g in got[:rank])
+        wrote = 0
+        if hi > lo:
+            if device:
+                os.lseek(pw["fd"], pos, os.SEEK_SET)
+                for first, part in gen.ctx.parts():
+                    _, _, nb = sim.write_fastq(part.struct, pw["fd"], first=lo + first)
+                    wrote += nb
+            else:
+                text, r2, _ = sim.fastq(b, first=lo)
+                view = memoryview(text)
+                while len(view):
+                    n = os.pwrite(pw["fd"], view, pos + wrote)
+                    view = view[n:]
+                    wrote += n
+        if wrote != nbytes:
+            raise RuntimeError("parallel writer: %d bytes written, %d expected" % (wrote, nbytes))
+        sim.skip_names(sum(g[0] for g in got[rank + 1:]))
+        pw["pos"] += sum(g[1] for g in got)
+        tot_reads += sum(g[0] for g in got)
+        tot_bases += sum(g[2] for g in got)
+        t3 = time.perf_counter()
+        acc["generate"] += t1 - t0
+        acc["exchange"] += t2 - t1
+        acc["write"] += t3 - t2
+    return tot_reads, tot_bases
 
 
 def chunk_bounds(descs, chunk_bases):
@@ -185,8 +275,13 @@ def _simulate_single_gpu(sim, total, limit, output, device, chunk_bases):
     return n_reads, n_bases
 
 
-def simulate(fasta, quantity, output, generate_factory=None, dist=None, rank=0, world=1, device=0, chunk_bases=1_000_000_000, **flags):
-    """Run `rustyread simulate`.  `output` is a binary file object (only used on rank 0).  Returns (reads, bases)."""
+def simulate(fasta, quantity, output, generate_factory=None, dist=None, rank=0, world=1, device=0, chunk_bases=1_000_000_000, output_path=None,
+             **flags):
+    """Run `rustyread simulate`.  `output` is a binary file object (only used on rank 0).  Returns (reads, bases).
+
+    world > 1 with `output_path` (a regular file every rank can open): every rank formats the records of its own shard
+    and writes them at their final offset with pwrite (parallel writer); otherwise the shards travel to rank 0, the
+    single writer.  Both produce the same bytes."""
     f = dict(FLAG_DEFAULTS)
     f.update({k: v for k, v in flags.items() if v is not None})
     if f["seed"] is None:
@@ -213,6 +308,16 @@ def simulate(fasta, quantity, output, generate_factory=None, dist=None, rank=0, 
         return _simulate_single_gpu(sim, total, limit, output, device, chunk_bases)
     gen = (generate_factory or (lambda s: DeviceGenerator(s, device)))(sim)
     produced, n_reads, n_bases = 0, 0, 0
+    pw = None
+    if world > 1 and output_path is not None:
+        import os
+
+        if rank == 0:
+            if output is not None:
+                output.flush()
+            os.close(os.open(output_path, os.O_WRONLY | os.O_CREAT | os.O_TRUNC, 0o644))
+        dist.barrier()
+        pw = dict(fd=os.open(output_path, os.O_WRONLY), pos=0)
     DT = (np.uint64, np.uint64, np.uint8, np.uint8, np.float64)
     while produced < total:  # src/simulate/mod.rs:153-214
         base_loop = min(limit, total - produced)
@@ -220,6 +325,11 @@ def simulate(fasta, quantity, output, generate_factory=None, dist=None, rank=0, 
         descs = sim.feed(base_loop)
         bounds = shard_bounds(descs, world)
         lo, hi = bounds[rank], bounds[rank + 1]
+        if world > 1 and output_path is not None:
+            r, b = _write_batch_in_place(sim, gen, descs, dist, rank, world, pw, chunk_bases)
+            n_reads += r
+            n_bases += b
+            continue
         mine = gen(descs[lo:hi])
         if world > 1:
             import torch
@@ -249,6 +359,14 @@ def simulate(fasta, quantity, output, generate_factory=None, dist=None, rank=0, 
             dist.broadcast(t, 0)
             if rank != 0:
                 sim.skip_names(int(t.item()))
-    if rank == 0:
+    if pw is not None:
+        import os
+        import sys
+
+        os.close(pw["fd"])
+        dist.barrier()
+        if os.environ.get("RUSTYREAD_B200_TIMING") and "acc" in pw:  # developer aid: where the wall clock of this rank went
+            print("rustyread_b200 timing rank %d (s): " % rank + ", ".join("%s %.3f" % kv for kv in pw["acc"].items()), file=sys.stderr)
+    elif rank == 0:
         output.flush()
     return n_reads, n_bases

@@ -585,8 +585,11 @@ def test_capacity_overflow_is_replanned_not_truncated(orc):
     ctx.close()
 
 
-def test_two_gpu_cli_matches_oracle(orc, rr, tmp_path):
-    """torchrun with 2 ranks (one process per GPU): sharded generation, single-writer FASTQ == the oracle's simulate()."""
+@pytest.mark.parametrize("mode", ["parallel", "parallel-rounds", "single"])
+def test_two_gpu_cli_matches_oracle(orc, rr, tmp_path, mode):
+    """torchrun with 2 ranks (one process per GPU): sharded generation; FASTQ == the oracle's simulate() with the parallel
+    writer (every rank streams its pieces to their final offsets; one or several rounds per batch) and with the single writer."""
+    import os
     import subprocess
     import sys
 
@@ -599,7 +602,12 @@ def test_two_gpu_cli_matches_oracle(orc, rr, tmp_path):
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1", "--master-port", "29541",
            "-m", "rustyread_b200", "simulate", "--reference", str(ref), "--quantity", "12x", "--seed", "21", "--error_model", "random",
            "--qscore_model", "random", "--output", str(out), "--number_base_store", "700K"]
-    r = subprocess.run(cmd, capture_output=True, text=True, cwd=helpers.ROOT, timeout=900)
+    env = dict(os.environ)
+    if mode == "single":
+        env["RUSTYREAD_B200_SINGLE_WRITER"] = "1"
+    if mode == "parallel-rounds":
+        env["RUSTYREAD_B200_CHUNK_BASES"] = "90000"
+    r = subprocess.run(cmd, capture_output=True, text=True, cwd=helpers.ROOT, timeout=900, env=env)
     assert r.returncode == 0, r.stderr[-3000:]
     text, stats = orc.simulate(dict(seed=21, quantity="12x", number_base_store="700K", threads=8), fasta, capture=True)
     assert out.read_text() == text and stats["reads"] > 50

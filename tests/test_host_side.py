@@ -185,7 +185,11 @@ def test_fastq_writer_matches_oracle_simulate(rr, orc, store):
         lens = (so[1:] - so[:-1]).astype(np.uint64)
         for lo, hi in ((0, half), (half, len(descs))):
             sb = capi.batch_struct_from_arrays(so[lo:hi + 1] - so[lo], lens[lo:hi], seq[int(so[lo]):int(so[hi])] if hi > lo else seq[:1], qual[int(so[lo]):int(so[hi])] if hi > lo else qual[:1], ident[lo:hi], 7)
+            words = sim.rng_words()
+            assert sim.fastq_bytes(lens[lo:hi], ident[lo:hi], first=lo)[1:] == (int(np.count_nonzero(lens[lo:hi] > 14)), int(sum(int(x) - 14 for x in lens[lo:hi] if x > 14)))
+            assert sim.rng_words() == words  # sizing draws nothing from main_rng
             t, r, bs = sim.fastq(sb, first=lo)
+            assert sim.fastq_bytes(lens[lo:hi], ident[lo:hi], first=lo) == (len(t), r, bs)
             out += t
             recs += r
             bases += bs

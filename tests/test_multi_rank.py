@@ -45,12 +45,14 @@ WORKER = textwrap.dedent('''
             seq, so = w.out("seq"); qual, _ = w.out("qual")
             return (so, (so[1:] - so[:-1]).astype(np.uint64), seq[:int(so[-1])], qual[:int(so[-1])], w.out_identity())
 
+    parallel = %(parallel)r
     out = io.BytesIO() if rank == 0 else None
     reads, bases = S.simulate(fasta, "10x", out, generate_factory=OracleGenerator, dist=dist, rank=rank, world=world, seed=9, length="2500,2200",
                               junk_reads=5.0, random_reads=5.0, chimera=10.0, glitches="900,25,25", error_model="random", qscore_model="random",
-                              number_base_store="300K")
+                              number_base_store="300K", output_path=%(out)r if parallel else None, chunk_bases=%(chunk)d)
     if rank == 0:
-        open(%(out)r, "wb").write(out.getvalue())
+        if not parallel:
+            open(%(out)r, "wb").write(out.getvalue())
         print("READS", reads, bases)
     dist.destroy_process_group()
 ''')
@@ -97,13 +99,18 @@ def test_compressed_inputs_are_sniffed_like_niffler(tmp_path):
         assert read_maybe_compressed(str(p)) == text
 
 
-def test_world_size_2_simulate_matches_single_process(orc, tmp_path):
+@pytest.mark.parametrize("parallel,world,chunk", [(False, 2, 10 ** 9), (True, 2, 10 ** 9), (True, 3, 40_000)])
+def test_world_size_2_simulate_matches_single_process(orc, tmp_path, parallel, world, chunk):
+    """Single writer (shards gathered on rank 0) and parallel writer (every rank formats its shard and pwrites it at its
+    final offset, read-name draws kept in step through skip_names; with 3 ranks in several rounds of pieces per batch):
+    same bytes as the oracle's single-process run."""
     fasta = helpers.random_fasta(orc, [70_000, 5_000], circular={1})
     fpath, opath, wpath = tmp_path / "ref.fa", tmp_path / "out.fq", tmp_path / "worker.py"
     fpath.write_text(fasta)
-    wpath.write_text(WORKER % dict(root=ROOT, fasta=str(fpath), out=str(opath)))
+    wpath.write_text(WORKER % dict(root=ROOT, fasta=str(fpath), out=str(opath), parallel=parallel, chunk=chunk))
     env = dict(os.environ, MASTER_ADDR="127.0.0.1")
-    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1", "--master-port", "29517", str(wpath)]
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=%d" % world, "--master-addr", "127.0.0.1",
+           "--master-port", str(29517 + 2 * world + int(parallel)), str(wpath)]
     r = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     params = dict(seed=9, length="2500,2200", quantity="10x", junk_reads=5, random_reads=5, chimera=10, glitches="900,25,25", threads=2,
