@@ -18,6 +18,9 @@ using namespace rr;
 
 #define RR_API extern "C" __attribute__((visibility("default")))
 
+static constexpr size_t READ_KERNEL_SMEM = (size_t)WARPS_PER_BLOCK * sizeof(WarpSmem);
+static_assert(READ_KERNEL_SMEM * RR_BLOCKS_PER_SM + 1024 * RR_BLOCKS_PER_SM <= 228 * 1024, "RR_BLOCKS_PER_SM blocks must fit the SM's shared memory");
+
 static std::string g_create_error;
 
 struct DevBuf {
@@ -174,6 +177,10 @@ RR_API int rr_create(int device, rr_ctx** out) {
   cudaDeviceProp prop;
   CK(cudaGetDeviceProperties(&prop, device));
   if (prop.major < 10) return fail(nullptr, RR_ERR_CUDA, "rr_create: kernels are built for sm_100a only");
+  // the read kernel's per-block shared memory (8 x WarpSmem) is dynamic: opt in past 48 KB, and keep the carve-out large
+  // enough for RR_BLOCKS_PER_SM resident blocks
+  CK(cudaFuncSetAttribute(rr_read_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)READ_KERNEL_SMEM));
+  CK(cudaFuncSetAttribute(rr_read_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
   ctx = new rr_ctx();
   ctx->device = device;
   ctx->n_sm = prop.multiProcessorCount;
@@ -531,7 +538,7 @@ static int plan(rr_ctx* ctx, Slot& sl) {
       gl = ng * (ctx->glitch_mean_size + 1.0);
       max_ng = std::max(max_ng, ng);
     }
-    // err / CIGAR leave the kernel in 128-byte chunks and the capacity test keeps two chunks of margin (flush_chunks)
+    // err / CIGAR leave the kernel in CHUNK-byte (256) chunks and the capacity test keeps two chunks of margin (flush_chunks)
     uint64_t ocap = align128(rcap + (uint64_t)std::ceil(target) + (uint64_t)gl + (uint64_t)(64 * sl.slack) + ALT_MAX + 16 + 3 * CHUNK);
     sl.h_raw_off[i + 1] = sl.h_raw_off[i] + align16(rcap + 16);
     sl.h_out_off[i + 1] = sl.h_out_off[i] + ocap;
@@ -656,7 +663,7 @@ static int enqueue(rr_ctx* ctx, Slot& sl) {
 
   CK(cudaMemsetAsync(sl.d_queue.p, 0, 16, ctx->stream));
   CK(cudaEventRecord(sl.ev[0], ctx->stream));
-  rr_read_kernel<<<sl.read_grid, WARPS_PER_BLOCK * 32, 0, ctx->stream>>>(P);
+  rr_read_kernel<<<sl.read_grid, WARPS_PER_BLOCK * 32, READ_KERNEL_SMEM, ctx->stream>>>(P);
   CK(cudaGetLastError());
   CK(cudaEventRecord(sl.ev[1], ctx->stream));
   rr_scan_kernel<<<1, 1024, 0, ctx->stream>>>(sl.d_err_len.as<uint64_t>(), sl.d_status.as<uint32_t>(), n, ctx->M.k,

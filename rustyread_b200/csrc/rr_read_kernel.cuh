@@ -199,7 +199,7 @@ __device__ __noinline__ StageOut stage_glitches(uint32_t ws32, uint32_t off, int
 // State of `changes.last()` plus the streamed stitch of sequence() (src/simulate/error.rs:219-246).
 // A Change only ever grows by appending to seq / cigar (merge, error.rs:105-152), and only the last
 // one can change, so err / CIGAR are written once, in order, as the walk proceeds: into the warp's staging rings
-// (WarpSmem::errb / cigb), from which complete 128-byte chunks leave for HBM.
+// (WarpSmem::errb / cigb), from which complete 256-byte chunks leave for HBM.
 // All positions are 32-bit: the host refuses reads whose raw capacity reaches 2^30 bases.
 // The last change is (le = its end in raw, lee = its end in err coordinates = begin + seq.len(), ledit).
 struct Stitch {
@@ -256,13 +256,13 @@ __device__ __forceinline__ void st_fail(Stitch& S, uint32_t status) {
 __device__ __forceinline__ uint4 eq16() { return make_uint4(0x3d3d3d3du, 0x3d3d3d3du, 0x3d3d3d3du, 0x3d3d3d3du); }
 
 // Sends the chunks completed since (e_old, c_old) to HBM and re-arms the CIGAR ring with '='.  Both rings are indexed
-// by absolute position modulo RING, so a chunk is 128-byte aligned on both sides.  The capacity test lives here: a
+// by absolute position modulo RING, so a chunk is CHUNK-aligned on both sides.  The capacity test lives here: a
 // read that comes within two chunks of its planned capacity is reported (the host re-plans the batch with more slack).
 __device__ __forceinline__ uint32_t flush_chunks(WarpSmem* ws, const ReadKernelParams& P, uint32_t ridx, uint32_t e_old, uint32_t e_new,
                                                  uint32_t c_old, uint32_t c_new, int lane) {
   __syncwarp();
   const uint64_t off = P.out_off[ridx];
-  if (lane < 8) {
+  if (lane < (int)(CHUNK / 16u)) {
     uint4* eg = reinterpret_cast<uint4*>(P.err + off);
     uint4* cg = reinterpret_cast<uint4*>(P.cig + off);
     for (uint32_t c = e_old & ~(CHUNK - 1u); c < (e_new & ~(CHUNK - 1u)); c += CHUNK)
@@ -563,7 +563,7 @@ __device__ __forceinline__ void process_read(const ReadKernelParams& P, WarpSmem
   W.S.le = W.S.lee = W.S.ledit = 0;
   __syncwarp();
   ws->st[ST_CAP] = (uint32_t)(P.out_off[ridx + 1] - P.out_off[ridx]);
-  if (lane < (int)(RING / 16)) *reinterpret_cast<uint4*>(&ws->cigb[16 * lane]) = eq16();
+  for (uint32_t i = lane; i < RING / 16u; i += 32) *reinterpret_cast<uint4*>(&ws->cigb[16u * i]) = eq16();
   __syncwarp();
 
   // ---- K3: error::sequence (src/simulate/error.rs:201-217) ----
@@ -742,7 +742,9 @@ __device__ __forceinline__ void process_read(const ReadKernelParams& P, WarpSmem
 }
 
 __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, RR_BLOCKS_PER_SM) rr_read_kernel(const __grid_constant__ ReadKernelParams P) {
-  __shared__ WarpSmem smem[WARPS_PER_BLOCK];
+  // dynamic shared memory (WARPS_PER_BLOCK x WarpSmem is past the 48 KB a kernel may declare statically)
+  extern __shared__ __align__(16) unsigned char smem_dyn[];
+  WarpSmem* smem = reinterpret_cast<WarpSmem*>(smem_dyn);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   WarpSmem* ws = &smem[warp];
   // fast-lane SMs (see ReadKernelParams): a wrong guess about the numbering of the SMs only changes who takes which read
