@@ -683,7 +683,7 @@ static int enqueue(rr_ctx* ctx, Slot& sl) {
   QP.packed_off = sl.d_packed_off.as<uint64_t>();
   QP.qual = sl.d_qual.as<uint8_t>();
   QP.status = P.status;
-  uint32_t qgrid = (uint32_t)std::min<uint64_t>((uint64_t)ctx->n_sm * 8, n);
+  uint32_t qgrid = (uint32_t)std::min<uint64_t>((uint64_t)ctx->n_sm * (2048 / Q_THREADS), n);  // every resident slot of the SMs, dynamic queue
   const bool q_k1 = ctx->Q.max_k == 1, q_cached = ctx->Q.n_dist <= QD_CACHE && ctx->Q.n_scores <= QS_CACHE;
   if (q_k1 && q_cached) rr_qscore_kernel<true, true><<<qgrid, Q_THREADS, 0, ctx->stream>>>(QP);
   else if (q_k1) rr_qscore_kernel<true, false><<<qgrid, Q_THREADS, 0, ctx->stream>>>(QP);

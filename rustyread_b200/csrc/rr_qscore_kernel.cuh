@@ -14,9 +14,13 @@
 
 namespace rr {
 
-constexpr int Q_THREADS = 256;
+#ifndef RR_Q_THREADS
+#define RR_Q_THREADS 128  // measured at 200x: 64 / 128 / 256 / 512 threads (all with 2048 resident threads per SM) -> 5.41 / 5.37 / 5.60 / 6.23 ms
+#endif
+constexpr int Q_THREADS = RR_Q_THREADS;
 constexpr int Q_PER_THREAD = 8;
-constexpr int Q_TILE = 2040;  // multiple of 8; 2 * 2040 + 15 words fit in 256 ChaCha blocks
+constexpr int Q_TILE = Q_THREADS * Q_PER_THREAD - 8;  // multiple of 8; 2 * Q_TILE + 15 words fit in Q_THREADS ChaCha blocks (one per thread)
+static_assert(2 * Q_TILE + 15 <= 16 * Q_THREADS, "a tile's draws must fit the blocks its threads generate");
 constexpr int Q_HALO = 8;     // (max_k - 1) / 2 <= 7
 constexpr uint32_t QD_CACHE = 128;   // distributions kept in shared memory when the whole model fits (random / ideal / small files)
 constexpr uint32_t QS_CACHE = 2048;  // ... and their scores
@@ -56,7 +60,10 @@ struct QscoreKernelParams {
 
 // K1: max_k == 1 (Quality::random / ideal): the window is the position itself.  CACHED: the whole model sits in shared memory.
 template <bool K1, bool CACHED>
-__global__ void __launch_bounds__(Q_THREADS) rr_qscore_kernel(const __grid_constant__ QscoreKernelParams P) {
+#ifndef RR_Q_MINB
+#define RR_Q_MINB (2048 / RR_Q_THREADS)  // 32 registers, 64 warps per SM: the kernel wants occupancy (256 threads: 8.7 / 6.4 / 5.8 / 5.6 ms at 200x for 1 / 4 / 6 / 8 blocks)
+#endif
+__global__ void __launch_bounds__(Q_THREADS, RR_Q_MINB) rr_qscore_kernel(const __grid_constant__ QscoreKernelParams P) {
   __shared__ __align__(16) uint32_t s_words[Q_THREADS * 16];
   __shared__ __align__(16) uint8_t s_cig[Q_HALO + Q_TILE + Q_HALO];
   __shared__ __align__(16) QDist s_dist[CACHED ? QD_CACHE : 1];
