@@ -502,6 +502,50 @@ def test_streaming_drain_matches_whole_batch_collect(orc):
     ctx.close()
 
 
+def test_collect_meta_sizes_records_before_the_first_part(orc, tmp_path):
+    """What the parallel multi-rank writer relies on, on one GPU: after rr_collect_begin, rr_collect_meta gives the whole
+    batch's lengths / identities, rr_sim_fastq_bytes sizes the records from them without touching main_rng, and the parts
+    written with writev at an offset of a shared file add up to exactly that many bytes = the text rr_sim_fastq produces."""
+    import os
+
+    import rustyread_b200.capi as capi
+
+    fasta = helpers.random_fasta(orc, [90_000, 4_000], circular={1})
+    sim = capi.Simulation(fasta, seed=11, length=(2500, 2000), junk_reads=4, random_reads=4, chimera=8)
+    ctx = capi.Context(0)
+    sim.attach(ctx)
+    ctx.debug_set_part_bytes(50_000)
+    descs = sim.feed(900_000)
+    lo = len(descs) // 3  # a shard that does not start at item 0
+    ctx.submit(descs[lo:])
+    n, bases, lens, ident = ctx.collect_begin()
+    assert n == len(descs) - lo
+    words = sim.rng_words()
+    nbytes, recs, nb = sim.fastq_bytes(lens, ident, first=lo)
+    assert sim.rng_words() == words and nb == bases and recs == int(np.count_nonzero(lens > 14))
+    path = tmp_path / "shared.fq"
+    prefix = b"x" * 123  # stands for the records of the ranks before this one
+    path.write_bytes(prefix)
+    fd = os.open(path, os.O_WRONLY)
+    os.lseek(fd, len(prefix), os.SEEK_SET)
+    wrote = 0
+    for first, part in ctx.parts():
+        wrote += sim.write_fastq(part.struct, fd, first=lo + first)[2]
+    os.close(fd)
+    assert wrote == nbytes and os.path.getsize(path) == len(prefix) + nbytes
+    # the same records through the in-memory formatter (a twin simulation: same seed, same main_rng position)
+    sim2 = capi.Simulation(fasta, seed=11, length=(2500, 2000), junk_reads=4, random_reads=4, chimera=8)
+    assert np.array_equal(sim2.feed(900_000), descs)
+    whole = ctx.generate(descs[lo:])
+    assert np.array_equal(whole.lengths, lens) and np.array_equal(whole.real_identity, ident)
+    text, r2, b2 = sim2.fastq(whole.struct, first=lo)
+    assert (len(text), r2, b2) == (nbytes, recs, nb)
+    assert path.read_bytes() == prefix + text
+    with pytest.raises(capi.RRError):
+        ctx.collect_begin()  # nothing submitted
+    ctx.close()
+
+
 def test_cli_simulate_matches_oracle(orc, tmp_path):
     """`python -m rustyread_b200 simulate` (the drop-in CLI) writes the same file as the oracle's simulate()."""
     import subprocess
