@@ -73,6 +73,27 @@ def test_shard_bounds_cover_and_balance():
     assert shard_bounds(d[:0], 4) == [0, 0, 0, 0, 0]
 
 
+def test_piece_bounds_are_round_major_and_bounded():
+    """Parallel writer: rounds x world contiguous pieces covering the batch in order, each about chunk_bases at most."""
+    import rustyread_b200.capi as capi
+    from rustyread_b200.simulate import piece_bounds
+
+    rs = np.random.RandomState(3)
+    d = np.zeros(5000, dtype=capi.DESC_DTYPE)
+    d["type"] = capi.RR_REAL
+    d["start"] = rs.randint(0, 10 ** 6, size=len(d))
+    d["end"] = d["start"] + rs.gamma(1.3, 11000, size=len(d)).astype(np.uint64)
+    total = int((d["end"] - d["start"]).sum()) + 64 * len(d)
+    for world, chunk in ((2, 10 ** 9), (3, 4_000_000), (8, 1_500_000)):
+        rounds, b = piece_bounds(d, world, chunk)
+        assert len(b) == rounds * world + 1 and b[0] == 0 and b[-1] == len(d) and all(x <= y for x, y in zip(b, b[1:]))
+        assert rounds == max(1, -(-total // (world * chunk)))
+        w = (d["end"] - d["start"]).astype(np.int64) + 64
+        loads = [int(w[b[i]:b[i + 1]].sum()) for i in range(rounds * world)]
+        assert max(loads) < 1.1 * total / (rounds * world) + 300_000
+    assert piece_bounds(d[:0], 4, 10 ** 6) == (1, [0, 0, 0, 0, 0])
+
+
 def test_flag_parsers():
     from rustyread_b200.simulate import parse_duo, parse_trio
 
