@@ -16,4 +16,5 @@ timeout 900 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__byte
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:rr_read_kernel -s 2 -c 1 -o $out/${tag}_read_kernel \
   python bench.py --steps 1 --warmup 3 --no-cpu-baseline > $out/${tag}_ncu_full.log 2>&1; echo "ncu full exit $?"
 ncu -i $out/${tag}_read_kernel.ncu-rep --page raw --csv > $out/${tag}_read_kernel_raw.csv 2>/dev/null
+timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > $out/${tag}_smoke.log 2>&1; tail -1 $out/${tag}_smoke.log
 ls -la $out
