@@ -360,9 +360,15 @@ ORC_API uint64_t orc_workload_feed(void* w_, uint64_t target, uint64_t max_items
   Workload* w = (Workload*)w_;
   w->items.clear();
   w->outs.clear();
-  Fragments fr(target, w->junk, w->random, w->chimera, w->refs, *w->length, *w->identity, w->main_rng);
-  WorkItem it;
-  while ((max_items == 0 || w->items.size() < max_items) && fr.next(it)) w->items.push_back(it);
+  try {
+    Fragments fr(target, w->junk, w->random, w->chimera, w->refs, *w->length, *w->identity, w->main_rng);
+    WorkItem it;
+    while ((max_items == 0 || w->items.size() < max_items) && fr.next(it)) w->items.push_back(it);
+  } catch (const std::exception& e) {  // a fragment no contig can host: the reference loops forever there
+    g_err = e.what();
+    w->items.clear();
+    return ~0ULL;
+  }
   return w->items.size();
 }
 // one descriptor = 12 u64: type, ref_idx, strand('+'=0,'-'=1,'*'=2), start, end, has_chimera, ctype, cref_idx, cstrand, cstart, cend, seed ; plus identity (f64) and length

@@ -382,6 +382,14 @@ struct Fragments {
     ReadType rt = get_read_type();
     size_t length = (size_t)lm.get_length(rng);
     if (rt == REAL) {
+      {  // the reference never leaves the loop below when no selectable contig can host the fragment: throw instead
+        bool possible = false;
+        for (size_t ri = 0; ri < refs.sequences.size(); ++ri) {
+          const Reference& r = refs.sequences[ri];
+          if (refs.prob[ri] > 0.0 && !(length >= r.seq.size() && r.circular)) { possible = true; break; }
+        }
+        if (!possible) throw std::runtime_error("generate_fragment: fragment fits no contig (all circular and shorter): the reference loops forever");
+      }
       auto ch = refs.choose_reference(rng);
       const Reference* ref = &refs.sequences[ch.first];
       while (length >= ref->seq.size() && ref->circular) {  // !fragment_is_possible

@@ -637,6 +637,15 @@ static uint64_t feed_fragment(rr_sim* s, bool* ok, uint32_t& type, uint32_t& ref
   uint64_t length = s->length.get(g);
   ref_idx = 0;
   if (type != RR_REAL) { strand = RR_NOSTRAND; start = 0; end = length; return length; }
+  // The reference re-draws the contig until the fragment fits (fragments.rs:80-85) and never leaves that loop when the
+  // length reaches every selectable contig and all of them are circular (many small plasmids with the default lengths):
+  // fail loudly instead of hanging.
+  {
+    bool possible = false;
+    for (const Contig& c : s->contigs)
+      if (c.weight > 0.0 && !(length >= c.seq.size() && c.circular)) { possible = true; break; }
+    if (!possible) { *ok = false; s->err = "fragment of " + std::to_string(length) + " bases fits no contig: every selectable contig is circular and shorter (the reference loops forever here; use a shorter --length or add a linear contig)"; return 0; }
+  }
   size_t idx;
   for (;;) {  // choose_reference (references.rs:83-92): strand from an i32 range (one u32 draw), then the contig
     strand = g.range_u32(0, 1) == 0 ? RR_PLUS : RR_MINUS;
@@ -658,6 +667,7 @@ static uint64_t feed_fragment(rr_sim* s, bool* ok, uint32_t& type, uint32_t& ref
 RR_API int rr_sim_feed(rr_sim* s, uint64_t base_loop, const rr_desc** descs, uint64_t* n) {
   if (!s || !descs || !n) return RR_ERR_ARG;
   s->items.clear();
+  s->err.clear();
   uint64_t target = base_loop;
   bool ok = true;
   while (target != 0) {  // Fragments::next (fragments.rs:132-164)
@@ -672,7 +682,8 @@ RR_API int rr_sim_feed(rr_sim* s, uint64_t base_loop, const rr_desc** descs, uin
     target = tt > target ? 0 : target - tt;
     d.identity = s->identity.get(s->rng);
     d.seed = s->rng.next_u64();
-    if (!ok) return sfail(s, RR_ERR_ARG, "rr_sim_feed: junk/random/chimera rate outside 0..100 (gen_bool panics in the reference)");
+    if (!ok) return sfail(s, RR_ERR_ARG, !s->err.empty() && s->err.rfind("fragment of ", 0) == 0 ? "rr_sim_feed: " + s->err
+                                         : std::string("rr_sim_feed: junk/random/chimera rate outside 0..100 (gen_bool panics in the reference)"));
     s->items.push_back(d);
   }
   *descs = s->items.data();

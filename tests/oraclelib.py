@@ -266,7 +266,11 @@ class Workload:
         return out
 
     def feed(self, target, max_items=0):
-        self.n = self.L.orc_workload_feed(self.h, target, max_items)
+        n = self.L.orc_workload_feed(self.h, target, max_items)
+        if n == 2 ** 64 - 1:
+            self.n = 0
+            raise RuntimeError(self.o.err())
+        self.n = n
         return self.n
 
     def items(self):

@@ -200,6 +200,38 @@ def test_fastq_writer_matches_oracle_simulate(rr, orc, store):
     assert out.decode() == text
 
 
+def test_fragment_that_fits_no_contig_fails_loudly_instead_of_hanging(rr, orc):
+    """fragments.rs:80-85 re-draws the contig until the fragment fits; with only circular contigs that are all shorter than
+    the drawn length the reference never leaves that loop (BASELINE config 5 with the default --length does this within
+    ~100 reads).  Product feeder and oracle both refuse loudly; with a length model that fits they agree item by item."""
+    import rustyread_b200.capi as capi
+
+    fasta = helpers.random_fasta(orc, [3000, 5000, 8000], circular={0, 1, 2})
+    sim = capi.Simulation(fasta, seed=1, length=(15000, 13000), small_plasmid_bias=True)
+    with pytest.raises(capi.RRError, match="fits no contig"):
+        sim.feed(2_000_000)
+    w = orc.workload(1)
+    w.set_length(15000.0, 13000.0)
+    w.set_references(fasta, adjusted=True, small_plasmid_bias=True)
+    w.set_identity(85.0, 95.0, 5.0)
+    w.set_rates(1.0, 1.0, 1.0)
+    with pytest.raises(RuntimeError, match="fits no contig"):
+        w.feed(2_000_000)
+    # one linear contig makes every length possible again
+    fasta2 = helpers.random_fasta(orc, [3000, 5000, 8000], circular={0, 1})
+    sim2 = capi.Simulation(fasta2, seed=1, length=(15000, 13000), small_plasmid_bias=True)
+    w2 = orc.workload(1)
+    w2.set_length(15000.0, 13000.0)
+    w2.set_references(fasta2, adjusted=True, small_plasmid_bias=True)
+    w2.set_identity(85.0, 95.0, 5.0)
+    w2.set_rates(1.0, 1.0, 1.0)
+    d = sim2.feed(300_000)
+    n = w2.feed(300_000)
+    od, oident, _ = w2.items()
+    pd, pident = capi.descs_to_item_table(d)
+    assert n == len(d) > 20 and np.array_equal(od, pd) and np.array_equal(oident, pident)
+
+
 def test_loader_rejects_what_the_reference_rejects(rr, orc):
     import rustyread_b200.capi as capi
 
