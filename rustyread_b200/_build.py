@@ -13,6 +13,9 @@ NVCC_FLAGS = [
     "--fmad=false",  # rustc never contracts a*b+c; bit parity of the f64 steps needs the same
     "-Xptxas", "-regUsageLevel=10",  # measured: qscore kernel 5.94 -> 5.78 ms, read kernel unchanged (experiments/README.md)
     "-Xcompiler", "-fPIC,-ffp-contract=off,-fvisibility=hidden",
+    # the CUDA runtime is linked dynamically (libcudart.so.12 is on the image's loader path): the shipped artefact then
+    # holds this library's own code only, not a copy of every runtime entry point
+    "--cudart", "shared",
     "-shared",
 ]
 
@@ -25,7 +28,8 @@ def stale():
     if not os.path.exists(LIB):
         return True
     t = os.path.getmtime(LIB)
-    deps = sources() + [os.path.join(os.path.dirname(HERE), "include", "rustyread_b200.h")]
+    inc = os.path.join(os.path.dirname(HERE), "include")
+    deps = sources() + [os.path.join(inc, "rustyread_b200.h"), os.path.join(inc, "rustyread_b200_host.h"), os.path.abspath(__file__)]
     return any(os.path.getmtime(s) > t for s in deps)
 
 

@@ -65,7 +65,7 @@ template <bool K1, bool CACHED>
 #endif
 __global__ void __launch_bounds__(Q_THREADS, RR_Q_MINB) rr_qscore_kernel(const __grid_constant__ QscoreKernelParams P) {
   __shared__ __align__(16) uint32_t s_words[Q_THREADS * 16];
-  __shared__ __align__(16) uint8_t s_cig[Q_HALO + Q_TILE + Q_HALO];
+  __shared__ __align__(16) uint8_t s_cig[Q_HALO + Q_THREADS * Q_PER_THREAD + Q_HALO];  // every thread loads its 8 ops (+ 8 on either side), also the ones past the tile
   __shared__ __align__(16) QDist s_dist[CACHED ? QD_CACHE : 1];
   __shared__ uint8_t s_scores[CACHED ? QS_CACHE : 1];
   __shared__ uint32_t s_warp_sum[Q_THREADS / 32];
@@ -230,8 +230,9 @@ __global__ void __launch_bounds__(Q_THREADS, RR_Q_MINB) rr_qscore_kernel(const _
       }
       rank0 += total;
     }
-    // mod.rs:284-287: the quality string is resized to the sequence length with '!'
-    for (uint32_t x = rank0 + tid; x < elen; x += Q_THREADS) qual[x] = '!';
+    // mod.rs:284-287: the quality string is resized to the sequence length with '!'; the padding up to the record's
+    // 16-byte boundary is zeroed like the sequence's (rr_pack_kernel), so that the drained arena is deterministic
+    for (uint32_t x = min(rank0, elen) + tid; x < ((elen + 15u) & ~15u); x += Q_THREADS) qual[x] = x < elen ? (uint8_t)'!' : (uint8_t)0;
   }
 }
 

@@ -40,6 +40,47 @@ def read_maybe_compressed(path):
     return raw
 
 
+def found_model(value, model_type, search_path=None):
+    """cli::simulate::found_model (src/cli/simulate.rs:130-159): an existing file is taken as it is; anything else is a
+    model NAME looked up as badread/<model_type>_models/<name>.gz along python's sys.path (where an installed badread
+    keeps `nanopore2020` and friends).  Like PathBuf::set_extension, a dotted name loses its last extension for `.gz`.
+    Raises FileNotFoundError (the reference: Cli::CantFoundModelPath) when the search fails."""
+    import os
+    import sys
+
+    if os.path.isfile(value):
+        return value
+    stem = value
+    base = os.path.basename(value)
+    if "." in base.lstrip("."):  # set_extension replaces the text after the last dot of the file name
+        stem = value[: len(value) - (len(base) - base.rindex("."))]
+    for root in (sys.path if search_path is None else search_path):
+        cand = os.path.join(root or ".", "badread", "%s_models" % model_type, stem + ".gz")
+        if os.path.isfile(cand):
+            return cand
+    raise FileNotFoundError("can't find %s model %r: not a file, and no badread/%s_models/%s.gz along python's sys.path "
+                            "(src/cli/simulate.rs:130-159); pass a model file, 'random' or (qscore) 'ideal'" % (model_type, value, model_type, stem))
+
+
+def agree_on_seed(dist, rank, world):
+    """No --seed: the reference seeds main_rng from the unix time in seconds (src/simulate/mod.rs:31-36).  Every rank of
+    a multi-process run replays the same serial feeder, so they must all use ONE seed: rank 0 reads the clock and
+    broadcasts it (ranks started around a second boundary would otherwise simulate different batches and the
+    parallel writer would stitch records of different simulations together, or hang on unequal round counts)."""
+    import time
+
+    seed = int(time.time())
+    if world > 1:
+        if dist is None:
+            raise ValueError("simulate: world > 1 without a torch.distributed handle and without --seed")
+        import torch
+
+        t = torch.tensor([seed if rank == 0 else 0], dtype=torch.int64)
+        dist.broadcast(t, 0)
+        seed = int(t.item())
+    return seed
+
+
 def parse_duo(text):  # cli::simulate::Duo, src/cli/simulate.rs:82-101
     parts = text.split(",")
     if len(parts) != 2 or not all(p.isdigit() for p in parts):
@@ -285,23 +326,18 @@ def simulate(fasta, quantity, output, generate_factory=None, dist=None, rank=0, 
     f = dict(FLAG_DEFAULTS)
     f.update({k: v for k, v in flags.items() if v is not None})
     if f["seed"] is None:
-        import time
+        f["seed"] = agree_on_seed(dist, rank, world)  # src/simulate/mod.rs:31-36
 
-        f["seed"] = int(time.time())  # src/simulate/mod.rs:31-36
-    for name in ("error_model", "qscore_model"):
-        if f[name] == "nanopore2020":
-            raise FileNotFoundError("model 'nanopore2020' lives in an installed badread package (src/cli/simulate.rs:130-159); "
-                                    "pass a model file, 'random' or (qscore) 'ideal'")
-
-    def model_text(v, builtins):
-        return v if v in builtins else read_maybe_compressed(v)
+    def model_text(v, kind, builtins):
+        return v if v in builtins else read_maybe_compressed(found_model(v, kind))
 
     sim = capi.Simulation(fasta, seed=f["seed"], length=parse_duo(f["length"]), identity=parse_trio(f["identity"]),
                           start_adapter=parse_duo(f["start_adapter"]), end_adapter=parse_duo(f["end_adapter"]),
                           start_adapter_seq=f["start_adapter_seq"], end_adapter_seq=f["end_adapter_seq"],
                           junk_reads=f["junk_reads"], random_reads=f["random_reads"], chimera=f["chimera"],
                           glitches=parse_trio(f["glitches"]), small_plasmid_bias=f["small_plasmid_bias"],
-                          error_model=model_text(f["error_model"], ("random",)), qscore_model=model_text(f["qscore_model"], ("random", "ideal")))
+                          error_model=model_text(f["error_model"], "error", ("random",)),
+                          qscore_model=model_text(f["qscore_model"], "qscore", ("random", "ideal")))
     total = sim.quantity(quantity)
     limit = sim.quantity(f["number_base_store"]) if f["number_base_store"] else total
     if world == 1 and generate_factory is None:

@@ -120,6 +120,64 @@ def test_compressed_inputs_are_sniffed_like_niffler(tmp_path):
         assert read_maybe_compressed(str(p)) == text
 
 
+def test_found_model_searches_badread_models_along_sys_path(tmp_path):
+    """cli::simulate::found_model (src/cli/simulate.rs:130-159): a file is itself; a name is badread/<type>_models/<name>.gz on sys.path."""
+    import gzip
+
+    from rustyread_b200.simulate import found_model, read_maybe_compressed
+
+    f = tmp_path / "my_model.txt"
+    f.write_text("x")
+    assert found_model(str(f), "error") == str(f)
+    site = tmp_path / "site-packages"
+    (site / "badread" / "error_models").mkdir(parents=True)
+    (site / "badread" / "qscore_models").mkdir(parents=True)
+    (site / "badread" / "error_models" / "nanopore2020.gz").write_bytes(gzip.compress(b"ACGTACG,0.5;ACGTACC,0.5;\n"))
+    got = found_model("nanopore2020", "error", search_path=["/nonexistent", str(site)])
+    assert got == str(site / "badread" / "error_models" / "nanopore2020.gz")
+    assert read_maybe_compressed(got).startswith(b"ACGTACG")
+    # PathBuf::set_extension: "a.b" becomes "a.gz"
+    (site / "badread" / "qscore_models" / "pacbio.gz").write_bytes(gzip.compress(b"q"))
+    assert found_model("pacbio.2016", "qscore", search_path=[str(site)]).endswith("qscore_models/pacbio.gz")
+    with pytest.raises(FileNotFoundError):
+        found_model("nanopore2020", "qscore", search_path=[str(site)])
+    with pytest.raises(FileNotFoundError):  # the CLI default without badread installed: the reference fails the same way
+        found_model("nanopore2020", "error", search_path=[])
+
+
+SEEDLESS_WORKER = textwrap.dedent('''
+    import os, sys, time
+    sys.path.insert(0, %(root)r)
+    import torch.distributed as dist
+    from rustyread_b200 import simulate as S
+    rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+    dist.init_process_group("gloo")
+    if rank == 1:
+        time.sleep(1.2)  # the ranks read the clock in different seconds
+    print("SEED", rank, S.agree_on_seed(dist, rank, world), flush=True)
+    dist.destroy_process_group()
+''')
+
+
+def test_ranks_agree_on_the_time_seed(tmp_path):
+    """No --seed under torchrun: rank 0 reads the clock, everybody uses its value (src/simulate/mod.rs:31-36 has one process)."""
+    wpath = tmp_path / "seedless.py"
+    wpath.write_text(SEEDLESS_WORKER % dict(root=ROOT))
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+           "--master-port", "29511", str(wpath)]
+    r = subprocess.run(cmd, env=dict(os.environ, MASTER_ADDR="127.0.0.1"), capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    import re
+
+    seeds = dict((int(a), int(b)) for a, b in re.findall(r"SEED (\d) (\d+)", r.stdout))
+    assert set(seeds) == {0, 1} and seeds[0] == seeds[1]
+    from rustyread_b200.simulate import agree_on_seed
+
+    assert abs(agree_on_seed(None, 0, 1) - __import__("time").time()) < 5
+    with pytest.raises(ValueError):
+        agree_on_seed(None, 1, 2)
+
+
 @pytest.mark.parametrize("parallel,world,chunk", [(False, 2, 10 ** 9), (True, 2, 10 ** 9), (True, 3, 40_000)])
 def test_world_size_2_simulate_matches_single_process(orc, tmp_path, parallel, world, chunk):
     """Single writer (shards gathered on rank 0) and parallel writer (every rank formats its shard and pwrites it at its
