@@ -74,6 +74,7 @@ struct rr_ctx {
   DevBuf d_em_index, d_em_alt_begin, d_em_alt_off, d_em_alt_bytes, d_em_cum, d_em_scale;
   DevBuf d_em_piece_begin, d_em_piece_off, d_em_piece_edits, d_em_piece_ops;
   DevBuf d_adapter;
+  DevBuf d_lcs_tab;
   DevBuf d_q_tab_off, d_q_tab, d_q_dist_off, d_q_scores, d_q_cum, d_q_scale, d_q_unit;
 
   // Up to two batches in flight (rr_submit / rr_collect): per-batch state lives in a slot; the big working
@@ -162,6 +163,76 @@ RR_API int rr_device_count(void) {
   return n;
 }
 
+// ---- table of small alignments (rr_device.cuh, LCS_MAX_SUM) ----------------------------------------------------------
+// One thread per (query, target) pair of a shape: alignment::align (src/alignment.rs:13-41) = LCS recurrence + the traceback
+// preference diag >= left && diag >= up -> diag, else up >= left -> I, else D (the same rule as host_align / the DP kernels).
+__global__ void __launch_bounds__(256) rr_lcs_table_kernel(uint32_t* __restrict__ tab, uint32_t m, uint32_t n) {
+  const uint32_t count = 1u << (2u * (m + n));
+  for (uint32_t key = blockIdx.x * blockDim.x + threadIdx.x; key < count; key += gridDim.x * blockDim.x) {
+    const uint32_t tcode = key & ((1u << (2u * n)) - 1u), qcode = key >> (2u * n);
+    uint8_t S[LCS_MAX_M + 1][LCS_MAX_N + 1];
+    for (uint32_t j = 0; j <= n; ++j) S[0][j] = 0;
+    for (uint32_t i = 1; i <= m; ++i) {
+      S[i][0] = 0;
+      const uint32_t qi = (qcode >> (2u * (i - 1u))) & 3u;
+      for (uint32_t j = 1; j <= n; ++j) {
+        const uint32_t eq = qi == ((tcode >> (2u * (j - 1u))) & 3u) ? 1u : 0u;
+        S[i][j] = (uint8_t)max((uint32_t)S[i - 1][j - 1] + eq, max((uint32_t)S[i - 1][j], (uint32_t)S[i][j - 1]));
+      }
+    }
+    uint32_t i = m, j = n, cnt = 0, rev = 0;  // ops in traceback order, 2 bits each
+    while (i > 0 || j > 0) {
+      uint32_t op;
+      if (i == 0) { op = 3; --j; }
+      else if (j == 0) { op = 2; --i; }
+      else {
+        const bool eq = ((qcode >> (2u * (i - 1u))) & 3u) == ((tcode >> (2u * (j - 1u))) & 3u);
+        const uint32_t dg = (uint32_t)S[i - 1][j - 1] + (eq ? 1u : 0u), up = S[i - 1][j], left = S[i][j - 1];
+        if (dg >= left && dg >= up) { op = eq ? 0u : 1u; --i; --j; }
+        else if (up >= left) { op = 2; --i; }
+        else { op = 3; --j; }
+      }
+      rev |= op << (2u * cnt);
+      ++cnt;
+    }
+    uint32_t fwd = 0;
+    for (uint32_t x = 0; x < cnt; ++x) fwd |= ((rev >> (2u * (cnt - 1u - x))) & 3u) << (2u * x);
+    tab[key] = fwd | (cnt << 28);
+  }
+}
+
+static int build_lcs_table(rr_ctx* ctx) {
+  std::vector<uint32_t> base(LCS_MAX_M * LCS_MAX_N, LCS_NO_TABLE);
+  uint64_t total = 0;
+  // RR_LCS_MIN (developer aid): smallest m + n that goes through the table; smaller windows keep the bit-vector DP
+  static const uint32_t min_sum = std::getenv("RR_LCS_MIN") ? (uint32_t)std::atoi(std::getenv("RR_LCS_MIN")) : LCS_MIN_SUM;
+  // shapes in order of m + n: the small windows, which take most of the lookups (76 % within 10 bases), sit together in
+  // the first 33 MiB of the table
+  for (uint32_t sum = std::max(2u, min_sum); sum <= LCS_MAX_SUM; ++sum) {
+    for (uint32_t m = 1; m <= LCS_MAX_M; ++m) {
+      const uint32_t n = sum - m;
+      if (n < 1 || n > LCS_MAX_N || m >= sum) continue;
+      base[(m - 1) * LCS_MAX_N + (n - 1)] = (uint32_t)total;
+      total += 1ull << (2 * sum);
+    }
+  }
+  if (total >= 0xffffffffull) return fail(ctx, RR_ERR_UNSUPPORTED, "alignment table: too many entries for 32-bit offsets");
+  ENSURE(ctx->d_lcs_tab, std::max<uint64_t>(total, 1) * 4);
+  CK(cudaMemcpyToSymbol(c_lcs_base, base.data(), base.size() * sizeof(uint32_t)));
+  for (uint32_t m = 1; m <= LCS_MAX_M; ++m)
+    for (uint32_t n = 1; n <= LCS_MAX_N; ++n) {
+      const uint32_t b = base[(m - 1) * LCS_MAX_N + (n - 1)];
+      if (b == LCS_NO_TABLE) continue;
+      const uint64_t count = 1ull << (2 * (m + n));
+      const uint32_t grid = (uint32_t)std::min<uint64_t>((count + 255) / 256, (uint64_t)ctx->n_sm * 32);
+      rr_lcs_table_kernel<<<grid, 256, 0, ctx->stream>>>(ctx->d_lcs_tab.as<uint32_t>() + b, m, n);
+      CK(cudaGetLastError());
+    }
+  CK(cudaStreamSynchronize(ctx->stream));
+  ctx->M.lcs_tab = ctx->d_lcs_tab.as<uint32_t>();
+  return RR_OK;
+}
+
 RR_API int rr_create(int device, rr_ctx** out) {
   rr_ctx* ctx = nullptr;
   if (!out) return fail(nullptr, RR_ERR_ARG, "rr_create: out is NULL");
@@ -190,6 +261,11 @@ RR_API int rr_create(int device, rr_ctx** out) {
     for (auto& ev : sl.ev) cudaEventCreate(&ev);
     cudaEventCreateWithFlags(&sl.done, cudaEventDisableTiming);
   }
+  if (build_lcs_table(ctx) != RR_OK) {
+    g_create_error = "rr_create: " + ctx->err;
+    rr_destroy(ctx);
+    return RR_ERR_CUDA;
+  }
   *out = ctx;
   return RR_OK;
 }
@@ -201,7 +277,7 @@ RR_API void rr_destroy(rr_ctx* ctx) {
   cudaStreamSynchronize(ctx->copy_stream);
   DevBuf* bufs[] = {&ctx->d_ref, &ctx->d_ref_off, &ctx->d_ref_circ, &ctx->d_em_index, &ctx->d_em_alt_begin, &ctx->d_em_alt_off,
                     &ctx->d_em_alt_bytes, &ctx->d_em_cum, &ctx->d_em_scale, &ctx->d_em_piece_begin, &ctx->d_em_piece_off, &ctx->d_em_piece_edits,
-                    &ctx->d_em_piece_ops, &ctx->d_adapter, &ctx->d_q_tab_off, &ctx->d_q_tab,
+                    &ctx->d_em_piece_ops, &ctx->d_adapter, &ctx->d_lcs_tab, &ctx->d_q_tab_off, &ctx->d_q_tab,
                     &ctx->d_q_dist_off, &ctx->d_q_scores, &ctx->d_q_cum, &ctx->d_q_scale, &ctx->d_q_unit, &ctx->d_raw, &ctx->d_err, &ctx->d_cig,
                     &ctx->d_sc_rows, &ctx->d_sc_ops, &ctx->d_sc_grec, &ctx->d_sc_gseq};
   for (auto* b : bufs) b->release();

@@ -467,6 +467,27 @@ __device__ __forceinline__ uint32_t add_change_reg(Walk& W, WarpSmem* ws, const 
   const bool emit = (S.flags & F_EMIT) != 0;
   uint32_t ed = 0, nops = 0;
   bool cold = false;
+  // A merge without a closed form whose window is small enough for the table of alignments (rr_device.cuh, LCS_MAX_SUM):
+  // the entry is fetched now, so that the L2 / HBM round trip overlaps the emission below.  Key: the 2-bit codes of the
+  // piece (lane es + i holds base i) above those of raw[rs, re) (lane j loads base j).
+  uint32_t lcs_e = 0;  // 0: not in the table (an entry always carries its op count in the top bits)
+  if (!cp.fast && add - 1u < LCS_MAX_M && tn - 1u < LCS_MAX_N) {
+    const uint32_t lbase = c_lcs_base[(add - 1u) * LCS_MAX_N + (tn - 1u)];
+    if (lbase != LCS_NO_TABLE) {
+      const uint32_t tb = (uint32_t)lane < tn ? (uint32_t)W.raw[cp.rs + lane] : (uint32_t)'A';
+      const bool inq = (uint32_t)lane >= es && (uint32_t)lane < olen;
+      bool clean = true;
+      if (S.flags & F_DIRTY) {  // bytes outside ACGT around: the table only knows the four bases ('A' 0x41, 'C' 0x43, 'G' 0x47, 'T' 0x54)
+        const uint32_t dq = (inq ? c : (uint32_t)'A') - 65u, dt = tb - 65u;
+        clean = !__any_sync(0xffffffffu, dq > 19u || dt > 19u || !((0x80045u >> dq) & (0x80045u >> dt) & 1u));
+      }
+      if (clean) {
+        uint32_t part = (uint32_t)lane < tn ? ((tb >> 1) & 3u) << (2u * (uint32_t)lane) : 0u;
+        if (inq) part |= ((c >> 1) & 3u) << (2u * (tn + (uint32_t)lane - es));
+        lcs_e = __ldg(P.M.lcs_tab + lbase + __reduce_or_sync(0xffffffffu, part));
+      }
+    }
+  }
   // One emission loop with a single flush site: the unchanged stretch before the change goes out 32 bases per step
   // (it is usually shorter than that), the piece and its ops go with the last step.
   uint32_t gap_left = emit ? cp.gap : 0u, gap_src = cp.gap_src;
@@ -510,7 +531,13 @@ __device__ __forceinline__ uint32_t add_change_reg(Walk& W, WarpSmem* ws, const 
         nops = add + tn;
         ed = nops;
         if (emit && (uint32_t)lane < nops) ws->cigb[(S.cig_len + lane) & (RING - 1u)] = add == 0 ? 'D' : 'I';
+      } else if (lcs_e) {  // a merge without a closed form, small enough for the table of alignments (fetched above)
+        nops = lcs_e >> 28;
+        ed = __popc((lcs_e | (lcs_e >> 1)) & 0x01555555u);  // ops other than '='
+        if (emit && (uint32_t)lane < nops) ws->cigb[(S.cig_len + lane) & (RING - 1u)] = (uint8_t)(0x4449583Du >> (8u * ((lcs_e >> (2u * lane)) & 3u)));
       } else {
+        // outside the table (2 % of these merges: more than LCS_MAX_SUM bases, or a byte outside ACGT): the register aligner.
+        // (Sending these to the out-of-line aligners instead was measured: 46.8 -> 49.2 ms, the parked walk state costs more.)
         uint64_t a = ~0ULL;
         if (add + tn <= 16u && add != 0 && tn != 0) {
           const uint32_t qc = __shfl_sync(0xffffffffu, c, (lane - 1 + (int)es) & 31);

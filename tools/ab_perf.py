@@ -1,4 +1,4 @@
-"""Developer tool: A/B timing of library builds on the same box.  usage: ab_perf.py cov lib1 lib2 ...  (prints min / median read-kernel ms)"""
+"""Developer tool: A/B timing of library builds on the same box.  usage: ab_perf.py cov lib1[@VAR=value,...] lib2 ...  (prints min / median read-kernel ms)"""
 import os, subprocess, sys
 cov = sys.argv[1]
 here = os.path.dirname(os.path.abspath(__file__))
@@ -25,6 +25,9 @@ print("read min %%.2f med %%.2f  qscore min %%.2f  (%%d runs)" %% (rk[0], rk[len
 for rnd in range(2):
     for lib in sys.argv[2:]:
         env = dict(os.environ)
+        lib, _, settings = lib.partition("@")  # lib.so@VAR=value,VAR2=value: environment of that run
+        for kv in filter(None, settings.split(",")):
+            env[kv.split("=")[0]] = kv.split("=")[1]
         if lib != "-": env["RR_LIB"] = lib
         out = subprocess.run([sys.executable, "-c", code, cov, "10"], env=env, capture_output=True, text=True)
-        print("%-40s %s" % (lib, out.stdout.strip() or out.stderr.strip()[-300:]), flush=True)
+        print("%-40s %s" % (lib.split("/")[-1] + ("@" + settings if settings else ""), out.stdout.strip() or out.stderr.strip()[-300:]), flush=True)
