@@ -27,14 +27,15 @@ plasmid_lens = [int(2000 * (25 ** rnd.random())) for _ in range(200)]
 plasmids = helpers.random_fasta(orc, plasmid_lens, circular=set(range(200)))
 cfg4 = dict(length=(50000.0, 40000.0), identity=(75.0, 90.0, 8.0), glitch=(2000.0, 50.0, 50.0), rates=(1.0, 1.0, 5.0))
 # with the default --length the reference (and so the feeder) never terminates on an all-circular reference whose contigs are
-# all shorter than a drawn fragment (fragments.rs:80-85); 6000,5000 keeps every draw below the 50 kbp plasmids in practice
-cfg5 = dict(rates=(10.0, 10.0, 1.0), small_plasmid_bias=True, length=(6000.0, 5000.0))
+# all shorter than a drawn fragment (fragments.rs:80-85); 4000,3000 keeps every draw of a 1-Gbase run below the largest plasmids
+# (6000,5000 still draws one such fragment within ~170 k reads)
+cfg5 = dict(rates=(10.0, 10.0, 1.0), small_plasmid_bias=True, length=(4000.0, 3000.0))
 CASES = [
     ("configs[0] ref5m 20x defaults random/random", ref5m, {}, 5_000_000 * 20),
     ("configs[1] ref5m 200x defaults random/random (bench line)", ref5m, {}, 5_000_000 * 200),
     ("ref5m 600x defaults random/random (3 Gbases in one batch; resident only)", ref5m, {}, 5_000_000 * 600),
     ("configs[3] ref5m 200x --length 50000,40000 --identity 75,90,8 --glitches 2000,50,50 --chimera 5", ref5m, cfg4, 5_000_000 * 200),
-    ("configs[4] 200 circular plasmids 2-50 kbp, 1 Gbase, --length 6000,5000 --small_plasmid_bias --junk_reads 10 --random_reads 10", plasmids, cfg5, 1_000_000_000),
+    ("configs[4] 200 circular plasmids 2-50 kbp, 1 Gbase, --length 4000,3000 --small_plasmid_bias --junk_reads 10 --random_reads 10", plasmids, cfg5, 1_000_000_000),
     ("ref5m 200x synthetic badread-scale FILE models (12k 7-mers x <=25 alternatives, CIGAR windows up to 9)", ref5m,
      dict(error_model=error_text, qscore_model=qscore_text), 5_000_000 * 200),
     ("ref5m 200x random error model, ideal qscores", ref5m, dict(qscore_model="ideal"), 5_000_000 * 200),
