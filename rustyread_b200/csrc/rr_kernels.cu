@@ -75,7 +75,7 @@ struct rr_ctx {
   DevBuf d_em_piece_begin, d_em_piece_off, d_em_piece_edits, d_em_piece_ops;
   DevBuf d_adapter;
   DevBuf d_lcs_tab;
-  DevBuf d_q_tab_off, d_q_tab, d_q_dist_off, d_q_scores, d_q_cum, d_q_scale, d_q_unit;
+  DevBuf d_q_tab_off, d_q_tab, d_q_dist_off, d_q_scores, d_q_cum, d_q_scale, d_q_unit, d_q_guide;
 
   // Up to two batches in flight (rr_submit / rr_collect): per-batch state lives in a slot; the big working
   // arenas (raw / err / cigar) and the per-warp scratch are shared because kernels of consecutive batches are
@@ -278,7 +278,7 @@ RR_API void rr_destroy(rr_ctx* ctx) {
   DevBuf* bufs[] = {&ctx->d_ref, &ctx->d_ref_off, &ctx->d_ref_circ, &ctx->d_em_index, &ctx->d_em_alt_begin, &ctx->d_em_alt_off,
                     &ctx->d_em_alt_bytes, &ctx->d_em_cum, &ctx->d_em_scale, &ctx->d_em_piece_begin, &ctx->d_em_piece_off, &ctx->d_em_piece_edits,
                     &ctx->d_em_piece_ops, &ctx->d_adapter, &ctx->d_lcs_tab, &ctx->d_q_tab_off, &ctx->d_q_tab,
-                    &ctx->d_q_dist_off, &ctx->d_q_scores, &ctx->d_q_cum, &ctx->d_q_scale, &ctx->d_q_unit, &ctx->d_raw, &ctx->d_err, &ctx->d_cig,
+                    &ctx->d_q_dist_off, &ctx->d_q_scores, &ctx->d_q_cum, &ctx->d_q_scale, &ctx->d_q_unit, &ctx->d_q_guide, &ctx->d_raw, &ctx->d_err, &ctx->d_cig,
                     &ctx->d_sc_rows, &ctx->d_sc_ops, &ctx->d_sc_grec, &ctx->d_sc_gseq};
   for (auto* b : bufs) b->release();
   for (auto& sl : ctx->slot) {
@@ -498,8 +498,22 @@ RR_API int rr_set_qscore_model(rr_ctx* ctx, uint32_t max_k, uint64_t n, const ui
     qd[i].nd_unit = (score_off[i + 1] - score_off[i]) | (unit[i] ? 0x80000000u : 0u);
     qd[i].scale = dist_ok[i] ? scale[i] : 0.0;
   }
+  // bounds of the per-draw search (QscoreModelDev::guide): the products are formed exactly as the kernel forms `chosen`
+  std::vector<uint16_t> guide(n * (Q_GUIDE + 1), 0);
+  for (uint64_t i = 0; i < n; ++i) {
+    const uint32_t a0 = score_off[i], nd = score_off[i + 1] - score_off[i];
+    if (!dist_ok[i] || nd == 0) continue;
+    if (nd > 65535) return fail(ctx, RR_ERR_UNSUPPORTED, "rr_set_qscore_model: a distribution with more than 65535 scores");
+    for (uint32_t g = 0; g < Q_GUIDE; ++g) {
+      const double x = ((double)g / (double)Q_GUIDE) * scale[i] + 0.0;
+      uint32_t c = 0;
+      while (c + 1 < nd && cum[a0 + c] <= x) ++c;  // partial sums are non-decreasing
+      guide[i * (Q_GUIDE + 1) + g] = (uint16_t)c;
+    }
+    guide[i * (Q_GUIDE + 1) + Q_GUIDE] = (uint16_t)(nd - 1);
+  }
   if (!upload(ctx, ctx->d_q_tab_off, tab_off) || !upload(ctx, ctx->d_q_tab, tab) || !upload(ctx, ctx->d_q_dist_off, qd) ||
-      !upload(ctx, ctx->d_q_scores, sc) || !upload(ctx, ctx->d_q_cum, cum))
+      !upload(ctx, ctx->d_q_scores, sc) || !upload(ctx, ctx->d_q_cum, cum) || !upload(ctx, ctx->d_q_guide, guide))
     return fail(ctx, RR_ERR_CUDA, "rr_set_qscore_model: upload failed");
   ctx->Q.max_k = max_k;
   ctx->Q.n_dist = (uint32_t)n;
@@ -509,6 +523,7 @@ RR_API int rr_set_qscore_model(rr_ctx* ctx, uint32_t max_k, uint64_t n, const ui
   ctx->Q.dist = ctx->d_q_dist_off.as<QDist>();
   ctx->Q.scores = ctx->d_q_scores.as<uint8_t>();
   ctx->Q.cum = ctx->d_q_cum.as<double>();
+  ctx->Q.guide = ctx->d_q_guide.as<uint16_t>();
   ctx->have_qscore = true;
   return RR_OK;
 }

@@ -40,7 +40,12 @@ struct QscoreModelDev {
   const QDist* dist;         // n_dist
   const uint8_t* scores;
   const double* cum;         // per dist: partial sums, last = total
+  // Per distribution Q_GUIDE + 1 bounds of the WeightedIndex search: guide[g] = number of partial sums <= (g / Q_GUIDE) * scale,
+  // guide[Q_GUIDE] = count - 1.  A draw u in [g / Q_GUIDE, (g + 1) / Q_GUIDE) selects an index in [guide[g], guide[g + 1]]
+  // (u * scale and the count are monotone), so the search over ~45 scores shrinks to the one or two that share a bucket.
+  const uint16_t* guide;
 };
+constexpr uint32_t Q_GUIDE = 16;
 
 struct QscoreKernelParams {
   QscoreModelDev Q;
@@ -216,7 +221,9 @@ __global__ void __launch_bounds__(Q_THREADS, RR_Q_MINB) rr_qscore_kernel(const _
           if (d.nd_unit >> 31) {
             lo = min((uint32_t)chosen, hi);  // partial sums are exactly 1, 2, ..: #{i : i + 1 <= chosen} = floor(chosen)
           } else {
-            uint32_t up = hi;
+            const uint16_t* gd = Q.guide + (size_t)dist * (Q_GUIDE + 1u) + (uint32_t)(u64_to_unit12(v) * (double)Q_GUIDE);
+            lo = gd[0];
+            uint32_t up = gd[1];
             while (lo < up) {
               uint32_t mid = (lo + up) >> 1;
               if (Q.cum[d.d0 + mid] <= chosen) lo = mid + 1; else up = mid;
