@@ -5,6 +5,8 @@
 
 namespace rr {
 
+enum : int { EM_RANDOM = 0, EM_PACKED = 1, EM_TABLES = 2 };  // Error::random(k) / file model in packed records / file model in plain tables
+
 // What an out-of-line stage hands back: the generator's offset (its base lives in shared memory) + one value.
 struct StageOut {
   uint64_t value;
@@ -458,11 +460,21 @@ __device__ __noinline__ uint32_t align_piece_cold(uint32_t ws32, int lane, const
 // tie-break), the edit then slides left while the neighbouring bases are equal (still matches), and where it stops the
 // two prefixes are identical, which forces X / I / D there and '=' before it.  Checked against the DP + tie-break
 // exhaustively for all k-mers up to k = 7 over 1-, 2- and 4-letter alphabets and for every piece offset.
+// `rec` (fk == 4 with packed tables, else 0): lane i < 16 holds word i of the alternative's record (DeviceModels::em_arec).
+// EM: the error model the kernel is instantiated for (EM_RANDOM / EM_PACKED / EM_TABLES); only EM_RANDOM and misses of the
+// file models take fk 1..3, only the file models take fk 4.
+template <int EM>
 __device__ __forceinline__ uint32_t add_change_reg(Walk& W, WarpSmem* ws, const ReadKernelParams& P, uint32_t ob, uint32_t oe, uint32_t c, uint32_t olen,
-                                                   uint32_t fk, uint32_t fep, uint32_t kb, int lane) {
+                                                   uint32_t fk, uint32_t fep, uint32_t kb, int lane, uint32_t rec = 0) {
   Stitch& S = W.S;
-  const ChangePlan cp = plan_change(S, W.L, ob, oe, olen, fk);
+  ChangePlan cp = plan_change(S, W.L, ob, oe, olen, fk);
   if (cp.contained) return 0;
+  uint32_t pk_ops = 0, pk_meta = 0;  // packed tables: the precomputed alignment of this alternative at piece offset es
+  if (EM == EM_PACKED && fk == 4 && cp.fast) {
+    pk_ops = __shfl_sync(0xffffffffu, rec, 4 + (int)(cp.es & 7u));
+    pk_meta = (__shfl_sync(0xffffffffu, rec, 12 + (int)((cp.es & 7u) >> 1)) >> (16u * (cp.es & 1u))) & 0xffffu;
+    if (cp.es > 7u || !(pk_meta & 0x8000u)) cp.fast = false;  // more than 16 ops: aligned like any other merge
+  }
   const uint32_t es = cp.es, add = olen - es, tn = cp.re - cp.rs;
   const bool emit = (S.flags & F_EMIT) != 0;
   uint32_t ed = 0, nops = 0;
@@ -506,7 +518,11 @@ __device__ __forceinline__ uint32_t add_change_reg(Walk& W, WarpSmem* ws, const 
         if ((uint32_t)lane >= es && (uint32_t)lane < olen) ws->errb[(S.err_len + lane - es) & (RING - 1u)] = (uint8_t)c;
         S.err_len += add;
       }
-      if (cp.fast && fk == 4) {  // table alternative against its own key: alignments precomputed at load time
+      if (EM == EM_PACKED && cp.fast && fk == 4) {  // table alternative against its own key, packed tables: the ops came with the record
+        nops = pk_meta & 31u;
+        ed = (pk_meta >> 5) & 31u;
+        if (emit && (uint32_t)lane < nops) ws->cigb[(S.cig_len + lane) & (RING - 1u)] = (uint8_t)(0x4449583Du >> (8u * ((pk_ops >> (2u * lane)) & 3u)));
+      } else if (EM == EM_TABLES && cp.fast && fk == 4) {  // ... unpacked tables: alignments precomputed at load time
         const DeviceModels& M = P.M;
         const uint32_t pi = M.em_piece_begin[fep] + es;
         const uint32_t o0 = M.em_piece_off[pi];
@@ -566,6 +582,7 @@ __device__ __forceinline__ uint32_t add_change_reg(Walk& W, WarpSmem* ws, const 
   return ed;
 }
 
+template <int EM>
 __device__ __forceinline__ void process_read(const ReadKernelParams& P, WarpSmem* ws, uint32_t ridx, int lane) {
   const DeviceModels& M = P.M;
   const uint32_t k = M.k;
@@ -674,17 +691,43 @@ __device__ __forceinline__ void process_read(const ReadKernelParams& P, WarpSmem
         uint32_t c = 0, olen, fk, fep;
         bool ok = true;
         int key = -1;
-        if (M.em_index) {  // 2-bit code of the k-mer; any byte outside ACGT misses the table
+        uint32_t koff = EM_NO_KEY;
+        if (EM != EM_RANDOM) {  // 2-bit code of the k-mer; any byte outside ACGT misses the table
           uint32_t part = 0, bad = 0;
           if ((uint32_t)lane < k) {
             uint32_t s = kb == 'A' ? 0u : kb == 'C' ? 1u : kb == 'G' ? 2u : kb == 'T' ? 3u : 4u;
             bad = s > 3u;
             part = (s & 3u) << (2 * (k - 1 - lane));
           }
-          uint32_t code = __reduce_or_sync(0xffffffffu, part);
-          if (!__any_sync(0xffffffffu, bad)) key = M.em_index[code];
+          const uint32_t code = __reduce_or_sync(0xffffffffu, part);
+          if (!__any_sync(0xffffffffu, bad)) {
+            if (EM == EM_PACKED) koff = __ldg(M.em_koff + code);  // packed tables: key record
+            else key = M.em_index[code];
+          }
         }
-        if (key >= 0) {  // one WeightedIndex draw over the alternatives of the k-mer (src/model/error.rs:96-100)
+        if (EM == EM_PACKED && koff != EM_NO_KEY) {  // one WeightedIndex draw over the alternatives of the k-mer (src/model/error.rs:96-100)
+          const uint8_t* kp = M.em_kblob + (size_t)koff * 16u;
+          const uint2 hd = __ldg(reinterpret_cast<const uint2*>(kp));  // alternatives, id of the first one
+          const double scale = __ldg(reinterpret_cast<const double*>(kp + 8));
+          const double* cump = reinterpret_cast<const double*>(kp + 16);
+          double cm = __ldg(cump + lane);  // the first 32 partial sums travel with the header (the blob is padded)
+          const uint32_t na = hd.x;
+          const uint64_t v2 = (uint64_t)ws->rng[W.off] | ((uint64_t)ws->rng[W.off + 1] << 32);  // first attempt: resident (HOT_FIRST)
+          W.off += 2;
+          const double chosen = u64_to_unit12(v2) * scale + 0.0;
+          uint32_t idx = 0;  // number of partial sums <= chosen among the first na - 1
+          for (uint32_t b = 0; b + 1 < na; b += 32) {
+            const uint32_t i = b + lane;
+            if (b) cm = (i + 1 < na) ? __ldg(cump + i) : 0.0;
+            idx += __popc(__ballot_sync(0xffffffffu, (i + 1 < na) && (cm <= chosen)));
+          }
+          fk = 4;
+          fep = hd.y + idx;  // global id of the chosen alternative
+          const uint32_t rec = (uint32_t)lane < EM_AREC_WORDS ? __ldg(M.em_arec + (size_t)fep * EM_AREC_WORDS + lane) : 0u;
+          olen = __shfl_sync(0xffffffffu, rec, 3) >> 24;
+          c = (__shfl_sync(0xffffffffu, rec, lane >> 2) >> (8u * ((uint32_t)lane & 3u))) & 0xffu;  // lane i = byte i (i < olen <= 15)
+          edits = add_change_reg<EM>(W, ws, P, W.pos, W.pos + k, c, olen, fk, fep, kb, lane, rec);
+        } else if (EM == EM_TABLES && key >= 0) {  // one WeightedIndex draw over the alternatives of the k-mer (src/model/error.rs:96-100)
           const uint32_t a0 = M.em_alt_begin[key], na = M.em_alt_begin[key + 1] - a0;
           const uint64_t v2 = (uint64_t)ws->rng[W.off] | ((uint64_t)ws->rng[W.off + 1] << 32);  // first attempt: resident (HOT_FIRST)
           W.off += 2;
@@ -701,7 +744,7 @@ __device__ __forceinline__ void process_read(const ReadKernelParams& P, WarpSmem
           olen = M.em_alt_off[fep + 1] - o0;
           if (olen <= 32u) {
             if ((uint32_t)lane < olen) c = M.em_alt_bytes[o0 + lane];
-            edits = add_change_reg(W, ws, P, W.pos, W.pos + k, c, olen, fk, fep, kb, lane);
+            edits = add_change_reg<EM>(W, ws, P, W.pos, W.pos + k, c, olen, fk, fep, kb, lane);
           } else {  // an alternative longer than a warp: through memory
             walk_save(ws, W);
             edits = add_change_cold(ws32, lane, P, W.pos, W.pos + k, M.em_alt_bytes + o0, olen);
@@ -732,7 +775,7 @@ __device__ __forceinline__ void process_read(const ReadKernelParams& P, WarpSmem
           }
           fk = kind;
           fep = ep;
-          edits = add_change_reg(W, ws, P, W.pos, W.pos + k, c, olen, fk, fep, kb, lane);
+          edits = add_change_reg<EM>(W, ws, P, W.pos, W.pos + k, c, olen, fk, fep, kb, lane);
         }
         W.S.flags &= ~F_REPLAYED;
       }
@@ -768,6 +811,9 @@ __device__ __forceinline__ void process_read(const ReadKernelParams& P, WarpSmem
   }
 }
 
+// One instantiation per kind of error model, so that the hot loop of each holds only its own path (the bench's Error::random
+// kernel carries no table code at all).
+template <int EM>
 __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, RR_BLOCKS_PER_SM) rr_read_kernel(const __grid_constant__ ReadKernelParams P) {
   // dynamic shared memory (WARPS_PER_BLOCK x WarpSmem is past the 48 KB a kernel may declare statically)
   extern __shared__ __align__(16) unsigned char smem_dyn[];
@@ -799,7 +845,7 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, RR_BLOCKS_PER_SM) rr_rea
     const uint32_t got = __shfl_sync(0xffffffffu, slot, 0);
     if (got == ~0u) break;
     if (fast ? got >= P.n_heavy : got < P.n_heavy) first_open = false;
-    process_read(P, ws, P.order[got], lane);
+    process_read<EM>(P, ws, P.order[got], lane);
     __syncwarp();
   }
 }
