@@ -251,7 +251,8 @@ RR_API int rr_create(int device, rr_ctx** out) {
   if (prop.major < 10) return fail(nullptr, RR_ERR_CUDA, "rr_create: kernels are built for sm_100a only");
   // the read kernel's per-block shared memory (8 x WarpSmem) is dynamic: opt in past 48 KB, and keep the carve-out large
   // enough for RR_BLOCKS_PER_SM resident blocks
-  for (auto* kern : {rr_read_kernel<EM_RANDOM>, rr_read_kernel<EM_PACKED>, rr_read_kernel<EM_TABLES>}) {
+  for (auto* kern : {rr_read_kernel<EM_RANDOM, 7>, rr_read_kernel<EM_PACKED, 7>, rr_read_kernel<EM_TABLES, 7>,
+                     rr_read_kernel<EM_RANDOM, 0>, rr_read_kernel<EM_PACKED, 0>, rr_read_kernel<EM_TABLES, 0>}) {
     CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)READ_KERNEL_SMEM));
     CK(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
   }
@@ -810,7 +811,10 @@ static int enqueue(rr_ctx* ctx, Slot& sl) {
 
   CK(cudaMemsetAsync(sl.d_queue.p, 0, 16, ctx->stream));
   CK(cudaEventRecord(sl.ev[0], ctx->stream));
-  auto* read_kernel = !ctx->M.em_index ? rr_read_kernel<EM_RANDOM> : ctx->M.em_koff ? rr_read_kernel<EM_PACKED> : rr_read_kernel<EM_TABLES>;
+  const bool k7 = ctx->M.k == 7;
+  auto* read_kernel = !ctx->M.em_index ? (k7 ? rr_read_kernel<EM_RANDOM, 7> : rr_read_kernel<EM_RANDOM, 0>)
+                      : ctx->M.em_koff ? (k7 ? rr_read_kernel<EM_PACKED, 7> : rr_read_kernel<EM_PACKED, 0>)
+                                       : (k7 ? rr_read_kernel<EM_TABLES, 7> : rr_read_kernel<EM_TABLES, 0>);
   read_kernel<<<sl.read_grid, WARPS_PER_BLOCK * 32, READ_KERNEL_SMEM, ctx->stream>>>(P);
   CK(cudaGetLastError());
   CK(cudaEventRecord(sl.ev[1], ctx->stream));

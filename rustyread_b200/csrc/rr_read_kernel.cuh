@@ -582,10 +582,11 @@ __device__ __forceinline__ uint32_t add_change_reg(Walk& W, WarpSmem* ws, const 
   return ed;
 }
 
-template <int EM>
+// KC: the model's k when the kernel is instantiated for it (7: Error::random and every badread model), 0 = read it from the model
+template <int EM, int KC>
 __device__ __forceinline__ void process_read(const ReadKernelParams& P, WarpSmem* ws, uint32_t ridx, int lane) {
   const DeviceModels& M = P.M;
-  const uint32_t k = M.k;
+  const uint32_t k = KC ? (uint32_t)KC : M.k;
   const uint32_t ws32 = smem_addr(ws);
   Walk W;
   {
@@ -813,7 +814,7 @@ __device__ __forceinline__ void process_read(const ReadKernelParams& P, WarpSmem
 
 // One instantiation per kind of error model, so that the hot loop of each holds only its own path (the bench's Error::random
 // kernel carries no table code at all).
-template <int EM>
+template <int EM, int KC>
 __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, RR_BLOCKS_PER_SM) rr_read_kernel(const __grid_constant__ ReadKernelParams P) {
   // dynamic shared memory (WARPS_PER_BLOCK x WarpSmem is past the 48 KB a kernel may declare statically)
   extern __shared__ __align__(16) unsigned char smem_dyn[];
@@ -845,7 +846,7 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, RR_BLOCKS_PER_SM) rr_rea
     const uint32_t got = __shfl_sync(0xffffffffu, slot, 0);
     if (got == ~0u) break;
     if (fast ? got >= P.n_heavy : got < P.n_heavy) first_open = false;
-    process_read<EM>(P, ws, P.order[got], lane);
+    process_read<EM, KC>(P, ws, P.order[got], lane);
     __syncwarp();
   }
 }
