@@ -3,7 +3,7 @@
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
 
-A step = one pass of the hot path (assemble -> glitches/error walk/alignment/stitch -> qscores -> pack)
+A step = one pass of the hot path (assemble -> glitches/error walk/alignment/stitch -> qscores + pack)
 over one batch of work items.  Workload = BASELINE.json configs[1]: synthetic 5 Mbp random single-contig
 reference, --quantity 200x, --seed 42, default length 15000,13000 / identity 85,95,5 / glitches
 10000,25,25 / junk,random,chimera 1,1,1, --error_model random --qscore_model random (the only models the
@@ -306,7 +306,7 @@ def main():
                 "frac": wi / read_kernel_s / (torch.cuda.get_device_properties(local_rank).multi_processor_count * 4 * mhz * 1e6),
                 "source": "smsp__inst_executed.sum from profiles/read_kernel_traffic.json; peak = SMs x 4 schedulers x sm_mhz"})(
                 ncu_traffic("warp_instructions_per_launch"), clocks.get("sm_mhz")),
-            "kernels_ms_per_step": {"rr_read_kernel": read_ms / args.steps, "rr_qscore_kernel(+scan)": q_ms / args.steps, "rr_pack_kernel": pack_ms / args.steps},
+            "kernels_ms_per_step": {"rr_read_kernel": read_ms / args.steps, "rr_scan_kernel + rr_qscore_kernel (draws the qualities and packs the sequences)": (q_ms + pack_ms) / args.steps},
         }
         if world == 1 and not args.no_cpu_baseline:
             threads = os.cpu_count() or 1

@@ -152,7 +152,7 @@ int rr_collect_meta(rr_ctx* ctx, const uint64_t** lengths, const double** real_i
 
 /* number of kernel launches issued by this context so far, and device milliseconds spent in the
  * last rr_run (CUDA events on the context's stream): [0] whole run, [1] read kernel (assemble +
- * glitches + error walk + alignment + stitch), [2] qscore kernel, [3] pack kernels */
+ * glitches + error walk + alignment + stitch), [2] scan + qscore kernel (which also packs the sequences), [3] 0 (the pack step no longer has a launch of its own) */
 uint64_t rr_kernel_launches(const rr_ctx* ctx);
 int rr_last_run_ms(const rr_ctx* ctx, float* ms4);
 /* bases emitted by the last run: sum over reads of max(0, len - 2k) for len > 14 (mod.rs:192-208) */

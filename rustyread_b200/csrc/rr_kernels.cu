@@ -780,7 +780,7 @@ static int prepare(rr_ctx* ctx, Slot& sl, uint64_t n, const rr_desc* descs) {
   return RR_OK;
 }
 
-// queue the four kernels of a batch on the compute stream; returns without waiting
+// queue the three kernels of a batch (read, scan, qscore + pack) on the compute stream; returns without waiting
 static int enqueue(rr_ctx* ctx, Slot& sl) {
   const uint32_t n = (uint32_t)sl.n;
   ReadKernelParams P{};
@@ -835,6 +835,8 @@ static int enqueue(rr_ctx* ctx, Slot& sl) {
   QP.packed_off = sl.d_packed_off.as<uint64_t>();
   QP.qual = sl.d_qual.as<uint8_t>();
   QP.status = P.status;
+  QP.err = P.err;
+  QP.seq = sl.d_seq.as<uint8_t>();
   uint32_t qgrid = (uint32_t)std::min<uint64_t>((uint64_t)ctx->n_sm * (2048 / Q_THREADS), n);  // every resident slot of the SMs, dynamic queue
   const bool q_k1 = ctx->Q.max_k == 1, q_cached = ctx->Q.n_dist <= QD_CACHE && ctx->Q.n_scores <= QS_CACHE;
   if (q_k1 && q_cached) rr_qscore_kernel<true, true><<<qgrid, Q_THREADS, 0, ctx->stream>>>(QP);
@@ -843,21 +845,11 @@ static int enqueue(rr_ctx* ctx, Slot& sl) {
   else rr_qscore_kernel<false, false><<<qgrid, Q_THREADS, 0, ctx->stream>>>(QP);
   CK(cudaGetLastError());
   CK(cudaEventRecord(sl.ev[2], ctx->stream));
-  PackKernelParams K{};
-  K.n_reads = n;
-  K.out_off = P.out_off;
-  K.packed_off = QP.packed_off;
-  K.err_len = P.err_len;
-  K.err = P.err;
-  K.seq = sl.d_seq.as<uint8_t>();
-  uint32_t pgrid = (uint32_t)std::min<uint64_t>((uint64_t)ctx->n_sm * 8, n);
-  rr_pack_kernel<<<pgrid, 256, 0, ctx->stream>>>(K);
-  CK(cudaGetLastError());
   CK(cudaEventRecord(sl.ev[3], ctx->stream));
   CK(cudaMemcpyAsync(sl.h_totals.p, sl.d_totals.p, 24, cudaMemcpyDeviceToHost, ctx->stream));
   CK(cudaMemcpyAsync(sl.h_status.p, sl.d_status.p, (size_t)n * 4, cudaMemcpyDeviceToHost, ctx->stream));
   CK(cudaEventRecord(sl.done, ctx->stream));
-  ctx->launches += 4;
+  ctx->launches += 3;
   sl.enqueued = true;
   return RR_OK;
 }

@@ -1,5 +1,5 @@
 // rustyread_b200 — K6: quality::generate_quality (src/simulate/quality.rs:14-38) +
-// Quality::get_qscore (src/model/quality.rs:113-133), and K7a: packing of the sequences.
+// Quality::get_qscore (src/model/quality.rs:113-133), and K7a: packing of the sequences (same kernel).
 //
 // get_qscore consumes exactly one u64 of the read's stream per non-'D' CIGAR position, so
 // position i with rank r (non-'D' positions before it) uses stream words q_cursor + 2r, +1.
@@ -58,9 +58,12 @@ struct QscoreKernelParams {
   const uint64_t* cig_len;
   const uint64_t* err_len;
   const uint64_t* q_cursor;
-  const uint64_t* packed_off;  // where read i's quality string goes
+  const uint64_t* packed_off;  // where read i's quality string (and packed sequence) goes
   uint8_t* qual;
   uint32_t* status;
+  // K7a, fused: the block that draws a read's qualities also moves its sequence from the err arena to the packed one
+  const uint8_t* err;
+  uint8_t* seq;
 };
 
 // K1: max_k == 1 (Quality::random / ideal): the window is the position itself.  CACHED: the whole model sits in shared memory.
@@ -105,6 +108,22 @@ __global__ void __launch_bounds__(Q_THREADS, RR_Q_MINB) rr_qscore_kernel(const _
     const uint64_t qcur = P.q_cursor[ridx];
     uint32_t key[8];
     chacha_key_from_u64(P.descs[ridx].seed, key);
+    {  // err arena -> packed sequence arena (both 16-byte aligned per read); the loads are in flight while the tiles below compute
+      const uint4* src = reinterpret_cast<const uint4*>(P.err + P.out_off[ridx]);
+      uint4* dst = reinterpret_cast<uint4*>(P.seq + P.packed_off[ridx]);
+      const uint32_t nv = (elen + 15u) / 16u;  // capacity is padded to 16 on both sides
+      for (uint32_t i = tid; i < nv; i += Q_THREADS) {
+        uint4 v = src[i];
+        if (16u * i + 16u > elen) {  // last word: the padding after the read is zeroed (what lies beyond err_len in the arena is stale staging data)
+          uint32_t w[4] = {v.x, v.y, v.z, v.w};
+          const uint32_t keep = elen - 16u * i;
+#pragma unroll
+          for (uint32_t j = 0; j < 4; ++j) w[j] = keep >= 4 * j + 4 ? w[j] : (keep > 4 * j ? (w[j] & ((1u << (8 * (keep - 4 * j))) - 1u)) : 0u);
+          v = make_uint4(w[0], w[1], w[2], w[3]);
+        }
+        dst[i] = v;
+      }
+    }
 
     uint32_t rank0 = 0;  // non-'D' positions before this tile
     for (uint32_t t0 = 0; t0 < n; t0 += Q_TILE) {
@@ -238,38 +257,8 @@ __global__ void __launch_bounds__(Q_THREADS, RR_Q_MINB) rr_qscore_kernel(const _
       rank0 += total;
     }
     // mod.rs:284-287: the quality string is resized to the sequence length with '!'; the padding up to the record's
-    // 16-byte boundary is zeroed like the sequence's (rr_pack_kernel), so that the drained arena is deterministic
+    // 16-byte boundary is zeroed like the sequence's (above), so that the drained arena is deterministic
     for (uint32_t x = min(rank0, elen) + tid; x < ((elen + 15u) & ~15u); x += Q_THREADS) qual[x] = x < elen ? (uint8_t)'!' : (uint8_t)0;
-  }
-}
-
-// err arena -> packed sequence arena (both 16-byte aligned per read)
-struct PackKernelParams {
-  uint32_t n_reads;
-  const uint64_t* out_off;
-  const uint64_t* packed_off;
-  const uint64_t* err_len;
-  const uint8_t* err;
-  uint8_t* seq;
-};
-
-__global__ void __launch_bounds__(256) rr_pack_kernel(const __grid_constant__ PackKernelParams P) {
-  for (uint32_t r = blockIdx.x; r < P.n_reads; r += gridDim.x) {
-    const uint64_t n = P.err_len[r];
-    const uint4* src = reinterpret_cast<const uint4*>(P.err + P.out_off[r]);
-    uint4* dst = reinterpret_cast<uint4*>(P.seq + P.packed_off[r]);
-    const uint64_t nv = (n + 15) / 16;  // capacity is padded to 16 on both sides
-    for (uint64_t i = threadIdx.x; i < nv; i += blockDim.x) {
-      uint4 v = src[i];
-      if (16 * i + 16 > n) {  // last word: the padding after the read is zeroed (what lies beyond err_len in the arena is stale staging data)
-        uint32_t w[4] = {v.x, v.y, v.z, v.w};
-        const uint32_t keep = (uint32_t)(n - 16 * i);
-#pragma unroll
-        for (uint32_t j = 0; j < 4; ++j) w[j] = keep >= 4 * j + 4 ? w[j] : (keep > 4 * j ? (w[j] & ((1u << (8 * (keep - 4 * j))) - 1u)) : 0u);
-        v = make_uint4(w[0], w[1], w[2], w[3]);
-      }
-      dst[i] = v;
-    }
   }
 }
 
