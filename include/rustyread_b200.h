@@ -91,6 +91,14 @@ int rr_device_count(void);
  * (references.rs:162-166).  The reverse complement (references.rs:27) is computed on the fly. */
 int rr_set_references(rr_ctx* ctx, uint64_t n, const uint8_t* const* seq, const uint64_t* len,
                       const uint8_t* circular);
+/* The same from DEVICE memory of the context's GPU: `device_bases` holds the n contigs back to back (sum of len bytes),
+ * e.g. the receive buffer of an NCCL broadcast from the rank that read the FASTA.  Copied device to device; the caller
+ * may free its buffer when the call returns. */
+int rr_set_references_device(rr_ctx* ctx, uint64_t n, const uint64_t* len, const uint8_t* circular,
+                             const void* device_bases);
+/* Device address and size of the context's reference arena (contigs back to back), valid until the references are set
+ * again or the context is destroyed: the send buffer of that broadcast. */
+int rr_references_device(const rr_ctx* ctx, const void** device_bases, uint64_t* bytes);
 
 /* model::Error (src/model/error.rs:19-22), AFTER loading: for key i (k bytes at keys + i*k) the
  * alternatives alt_begin[i] .. alt_begin[i+1], alternative j = alt_bytes[alt_off[j] .. alt_off[j+1])

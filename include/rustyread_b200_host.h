@@ -54,8 +54,19 @@ uint32_t rr_sim_k(const rr_sim* s);
 /* Quantity::from_str + number_of_base (src/cli/simulate.rs:12-80): "50", "50K", "50M", "50G", "50x"; -1 on error */
 int64_t rr_quantity_to_bases(const char* text, uint64_t genome_length);
 
+/* The same session without the bases: contig ids, lengths, circular flags and header weights (depth= x length) as
+ * rr_sim_contig_index reports them for a session made from FASTA text.  main_rng is drawn from in the same order
+ * (adjust_depth needs lengths only), so the feeder and the writer of such a session are indistinguishable from the
+ * original's.  For the ranks of a multi-GPU run that receive the reference device to device (rr_sim_attach_device)
+ * instead of parsing the FASTA again. */
+int rr_sim_create_indexed(const rr_sim_params* p, uint64_t n, const char* const* ids, const uint64_t* lengths, const uint8_t* circular,
+                          const double* weights, rr_sim** out);
+int rr_sim_contig_index(const rr_sim* s, uint64_t i, const char** id, uint64_t* length, int* circular, double* weight);
+
 /* References + the four models -> device context */
 int rr_sim_attach(const rr_sim* s, rr_ctx* ctx);
+/* ... with the concatenated bases of all contigs already in device memory of the context's GPU (rr_set_references_device) */
+int rr_sim_attach_device(const rr_sim* s, rr_ctx* ctx, const void* device_bases);
 
 /* One batch of the Fragments iterator for `base_loop` bases (mod.rs:153-170).  The returned array is owned by
  * the session and valid until the next rr_sim_feed. */

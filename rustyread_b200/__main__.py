@@ -37,13 +37,20 @@ def main(argv=None):
         import torch.distributed as dist
 
         dist.init_process_group("gloo")  # shard results travel host to host; the data path itself has no collective
-    fasta = sim_mod.read_maybe_compressed(a.reference)  # niffler: plain, gz, bz2 or xz by magic number
+    # Several ranks: rank 0 alone reads and parses the reference; the others get its index and receive the bases device to
+    # device over NVLink (simulate.shared_reference_context).  RUSTYREAD_B200_NO_SHARED_REFERENCE=1: every rank reads the file.
+    share = world > 1 and not os.environ.get("RUSTYREAD_B200_NO_SHARED_REFERENCE")
+    if share:
+        import torch
+
+        share = torch.cuda.is_available() and dist.is_nccl_available()
+    fasta = sim_mod.read_maybe_compressed(a.reference) if (rank == 0 or not share) else None  # niffler: plain, gz, bz2 or xz by magic number
     out = (open(a.output, "wb") if a.output else sys.stdout.buffer) if rank == 0 else None
     flags = {k: getattr(a, k) for k in d}
     chunk = int(os.environ.get("RUSTYREAD_B200_CHUNK_BASES", "1000000000"))  # device chunk size inside one reference batch
     # several ranks + a regular output file: every rank writes its own records in place (RUSTYREAD_B200_SINGLE_WRITER=1: gather on rank 0)
     par = a.output if (world > 1 and a.output and not os.environ.get("RUSTYREAD_B200_SINGLE_WRITER")) else None
-    reads, bases = sim_mod.simulate(fasta, a.quantity, out, dist=dist, rank=rank, world=world, device=local, chunk_bases=chunk, output_path=par, **flags)
+    reads, bases = sim_mod.simulate(fasta, a.quantity, out, dist=dist, rank=rank, world=world, device=local, chunk_bases=chunk, output_path=par, share_reference=share, **flags)
     if rank == 0 and a.verbosity:
         print("wrote %d reads, %d bases" % (reads, bases), file=sys.stderr)
     if os.environ.get("RUSTYREAD_B200_TIMING"):

@@ -40,6 +40,8 @@ EXPORTS = {
     "rr_last_error": (C.c_char_p, [C.c_void_p]),
     "rr_device_count": (C.c_int, []),
     "rr_set_references": (C.c_int, [C.c_void_p, C.c_uint64, C.POINTER(C.c_void_p), u64p, C.c_void_p]),
+    "rr_set_references_device": (C.c_int, [C.c_void_p, C.c_uint64, u64p, C.c_void_p, C.c_void_p]),
+    "rr_references_device": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), u64p]),
     "rr_set_error_model": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "rr_set_qscore_model": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "rr_set_adapter": (C.c_int, [C.c_void_p, C.c_char_p, C.c_uint64, C.c_char_p, C.c_uint64, C.c_double, C.c_double, C.c_double, C.c_double]),
@@ -151,6 +153,12 @@ class Context:
         lens = (C.c_uint64 * n)(*[len(s) for s in seqs])
         circ = (C.c_uint8 * n)(*[1 if (circular and circular[i]) else 0 for i in range(n)])
         self._ck(self.lib.dll.rr_set_references(self.h, n, ptrs, lens, circ))
+
+    def references_device(self):
+        """(device address, bytes) of the reference arena: contigs back to back (the send buffer of a broadcast)."""
+        ptr, n = C.c_void_p(), C.c_uint64()
+        self._ck(self.lib.dll.rr_references_device(self.h, C.byref(ptr), C.byref(n)))
+        return int(ptr.value or 0), int(n.value)
 
     def set_error_model_random(self, k=7):
         """model::Error::random(k) — src/model/error.rs:85-90."""
@@ -373,6 +381,9 @@ HOST_EXPORTS = {
     "rr_sim_k": (C.c_uint32, [C.c_void_p]),
     "rr_quantity_to_bases": (C.c_int64, [C.c_char_p, C.c_uint64]),
     "rr_sim_attach": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "rr_sim_attach_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
+    "rr_sim_create_indexed": (C.c_int, [C.POINTER(rr_sim_params), C.c_uint64, C.POINTER(C.c_char_p), u64p, C.c_void_p, f64p, C.POINTER(C.c_void_p)]),
+    "rr_sim_contig_index": (C.c_int, [C.c_void_p, C.c_uint64, C.POINTER(C.c_char_p), u64p, C.POINTER(C.c_int), f64p]),
     "rr_sim_feed": (C.c_int, [C.c_void_p, C.c_uint64, C.POINTER(C.c_void_p), u64p]),
     "rr_sim_fastq": (C.c_int, [C.c_void_p, C.POINTER(rr_batch), C.c_uint64, C.POINTER(C.c_void_p), u64p, u64p, u64p]),
     "rr_sim_write_fastq": (C.c_int, [C.c_void_p, C.POINTER(rr_batch), C.c_uint64, C.c_int, u64p, u64p, u64p]),
@@ -395,7 +406,7 @@ class Simulation:
                  start_adapter=(90, 60), end_adapter=(50, 20),
                  start_adapter_seq="AATGTACTTCGTTCAGTTACGTATTGCT", end_adapter_seq="GCAATACGTAACTGAACGAAGT",
                  junk_reads=1, random_reads=1, chimera=1, glitches=(10000, 25, 25), small_plasmid_bias=False,
-                 error_model="random", qscore_model="random", lib=None):
+                 error_model="random", qscore_model="random", lib=None, index=None):
         self.lib = lib or load_library()
         if isinstance(fasta, str):
             fasta = fasta.encode()
@@ -417,7 +428,15 @@ class Simulation:
         p.error_model, p.error_model_len = em, (len(em) if em else 0)
         p.qscore_model, p.qscore_model_len = qm, len(qm)
         h = C.c_void_p()
-        rc = self.lib.dll.rr_sim_create(C.byref(p), fasta, len(fasta), C.byref(h))
+        if index is not None:  # contigs without bases: [(id, length, circular, header weight)], see contig_index()
+            n = len(index)
+            ids = (C.c_char_p * n)(*[i[0].encode("utf-8", "surrogateescape") for i in index])
+            lens = (C.c_uint64 * n)(*[int(i[1]) for i in index])
+            circ = (C.c_uint8 * n)(*[1 if i[2] else 0 for i in index])
+            wts = (C.c_double * n)(*[float(i[3]) for i in index])
+            rc = self.lib.dll.rr_sim_create_indexed(C.byref(p), n, ids, lens, circ, wts, C.byref(h))
+        else:
+            rc = self.lib.dll.rr_sim_create(C.byref(p), fasta, len(fasta), C.byref(h))
         if rc:
             raise RRError(rc, self.lib.dll.rr_sim_last_error(None).decode())
         self.h = h
@@ -445,9 +464,23 @@ class Simulation:
             raise RRError(2, "cannot parse quantity %r" % text)
         return int(v)
 
-    def attach(self, ctx):
-        self._ck(self.lib.dll.rr_sim_attach(self.h, ctx.h))
+    def attach(self, ctx, device_bases=None):
+        """References + models -> device context; device_bases: device address of the concatenated contigs when they are
+        already on the context's GPU (a session made from an index has no host copy)."""
+        if device_bases is None:
+            self._ck(self.lib.dll.rr_sim_attach(self.h, ctx.h))
+        else:
+            self._ck(self.lib.dll.rr_sim_attach_device(self.h, ctx.h, C.c_void_p(device_bases)))
         ctx.k = self.k
+
+    def contig_index(self):
+        """[(id, length, circular, header weight = depth x length)] — all a session needs of the reference besides the bases."""
+        out = []
+        for i in range(self.lib.dll.rr_sim_n_refs(self.h)):
+            rid, ln, circ, w = C.c_char_p(), C.c_uint64(), C.c_int(), C.c_double()
+            self._ck(self.lib.dll.rr_sim_contig_index(self.h, i, C.byref(rid), C.byref(ln), C.byref(circ), C.byref(w)))
+            out.append((rid.value.decode("utf-8", "surrogateescape"), int(ln.value), bool(circ.value), float(w.value)))
+        return out
 
     def feed(self, base_loop):
         """One batch of the Fragments iterator; returns a numpy array of DESC_DTYPE (a copy)."""

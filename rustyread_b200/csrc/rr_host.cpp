@@ -199,9 +199,11 @@ struct Weighted {
 
 struct Contig {
   std::string id;
-  std::string seq;
+  std::string seq;       // empty in a session made from an index (rr_sim_create_indexed): the bases live on the device only
+  uint64_t len = 0;      // number of bases
   bool circular = false;
-  double weight = 0;
+  double weight = 0;     // depth x length, then adjusted (References::adjust_depth)
+  double weight0 = 0;    // depth x length as read from the header
 };
 
 // ---- MD5 (RFC 1321) for Uuid::new_v3 ------------------------------------------------------------------------------------
@@ -342,7 +344,8 @@ static const char* parse_fasta(std::string_view text, std::vector<Contig>& out) 
       }
     }
     cur.circular = desc.find("circular=true") != std::string::npos;
-    cur.weight = w * (double)cur.seq.size();
+    cur.len = cur.seq.size();
+    cur.weight = cur.weight0 = w * (double)cur.seq.size();
     out.push_back(std::move(cur));
     return nullptr;
   };
@@ -533,8 +536,10 @@ RR_API int64_t rr_quantity_to_bases(const char* text, uint64_t genome) {
   return (int64_t)(cov ? v * genome : v * mul);
 }
 
-RR_API int rr_sim_create(const rr_sim_params* p, const char* fasta, uint64_t fasta_len, rr_sim** out) {
-  if (!p || !fasta || !out) return sfail(nullptr, RR_ERR_ARG, "rr_sim_create: NULL argument");
+// Everything of simulate() up to the batch loop (mod.rs:28-127), in the reference's main_rng order; `fill` supplies the contigs
+// (from FASTA text, or from an index when the bases are already on the device).
+template <class Fill>
+static int create_session(const rr_sim_params* p, rr_sim** out, Fill fill) {
   *out = nullptr;
   rr_sim* s = new rr_sim();
   auto bail = [&](const std::string& m) { int rc = sfail(nullptr, RR_ERR_ARG, m); delete s; return rc; };
@@ -543,13 +548,13 @@ RR_API int rr_sim_create(const rr_sim_params* p, const char* fasta, uint64_t fas
   s->end_adapter = p->end_adapter_seq ? p->end_adapter_seq : "";
   s->rng = HostRng(p->seed);                                                             // mod.rs:28-37
   if (const char* m = s->length.init(p->length_mean, p->length_stdev)) return bail(m);  // mod.rs:40
-  if (const char* m = parse_fasta(std::string_view(fasta, fasta_len), s->contigs)) return bail(m);
+  if (const char* m = fill(s->contigs)) return bail(m);
   {  // References::adjust_depth (references.rs:95-132): 100 000 lengths from main_rng, always
     std::vector<uint64_t> lens(100000);
     uint64_t total = 0;
     for (auto& l : lens) { l = s->length.get(s->rng); total += l; }
     for (auto& c : s->contigs) {
-      uint64_t rl = c.seq.size();
+      uint64_t rl = c.len;
       if (!p->small_plasmid_bias && c.circular) {
         uint64_t pass = 0;
         for (uint64_t l : lens) if (l <= rl) pass += l;
@@ -588,9 +593,41 @@ RR_API int rr_sim_create(const rr_sim_params* p, const char* fasta, uint64_t fas
   return RR_OK;
 }
 
+RR_API int rr_sim_create(const rr_sim_params* p, const char* fasta, uint64_t fasta_len, rr_sim** out) {
+  if (!p || !fasta || !out) return sfail(nullptr, RR_ERR_ARG, "rr_sim_create: NULL argument");
+  return create_session(p, out, [&](std::vector<Contig>& c) { return parse_fasta(std::string_view(fasta, fasta_len), c); });
+}
+
+RR_API int rr_sim_create_indexed(const rr_sim_params* p, uint64_t n, const char* const* ids, const uint64_t* lengths, const uint8_t* circular,
+                                 const double* weights, rr_sim** out) {
+  if (!p || !out || !ids || !lengths || !circular || !weights) return sfail(nullptr, RR_ERR_ARG, "rr_sim_create_indexed: NULL argument");
+  return create_session(p, out, [&](std::vector<Contig>& c) -> const char* {
+    if (n == 0) return "reference: no sequence found";
+    for (uint64_t i = 0; i < n; ++i) {
+      Contig x;
+      x.id = ids[i] ? ids[i] : "";
+      x.len = lengths[i];
+      x.circular = circular[i] != 0;
+      x.weight = x.weight0 = weights[i];
+      c.push_back(std::move(x));
+    }
+    return nullptr;
+  });
+}
+
+RR_API int rr_sim_contig_index(const rr_sim* s, uint64_t i, const char** id, uint64_t* length, int* circular, double* weight) {
+  if (!s || i >= s->contigs.size()) return RR_ERR_ARG;
+  const Contig& c = s->contigs[i];
+  if (id) *id = c.id.c_str();
+  if (length) *length = c.len;
+  if (circular) *circular = c.circular;
+  if (weight) *weight = c.weight0;
+  return RR_OK;
+}
+
 RR_API uint64_t rr_sim_genome_length(const rr_sim* s) {
   uint64_t t = 0;
-  if (s) for (auto& c : s->contigs) t += c.seq.size();
+  if (s) for (auto& c : s->contigs) t += c.len;
   return t;
 }
 RR_API uint32_t rr_sim_k(const rr_sim* s) { return s ? s->k : 0; }
@@ -599,21 +636,29 @@ RR_API uint64_t rr_sim_rng_words(const rr_sim* s) { return s ? s->rng.words : 0;
 RR_API const uint8_t* rr_sim_ref(const rr_sim* s, uint64_t i, uint64_t* len, int* circular, double* weight, const char** id) {
   if (!s || i >= s->contigs.size()) return nullptr;
   const Contig& c = s->contigs[i];
-  if (len) *len = c.seq.size();
+  if (len) *len = c.len;
   if (circular) *circular = c.circular;
   if (weight) *weight = c.weight;
   if (id) *id = c.id.c_str();
   return (const uint8_t*)c.seq.data();
 }
 
-RR_API int rr_sim_attach(const rr_sim* s_, rr_ctx* ctx) {
-  rr_sim* s = const_cast<rr_sim*>(s_);
+static int attach(rr_sim* s, rr_ctx* ctx, const void* device_bases) {
   if (!s || !ctx) return RR_ERR_ARG;
   std::vector<const uint8_t*> ptr;
   std::vector<uint64_t> len;
   std::vector<uint8_t> circ;
-  for (auto& c : s->contigs) { ptr.push_back((const uint8_t*)c.seq.data()); len.push_back(c.seq.size()); circ.push_back(c.circular); }
-  int rc = rr_set_references(ctx, ptr.size(), ptr.data(), len.data(), circ.data());
+  bool have_bases = true;
+  for (auto& c : s->contigs) {
+    ptr.push_back((const uint8_t*)c.seq.data());
+    len.push_back(c.len);
+    circ.push_back(c.circular);
+    have_bases = have_bases && c.seq.size() == c.len;
+  }
+  int rc;
+  if (device_bases) rc = rr_set_references_device(ctx, len.size(), len.data(), circ.data(), device_bases);
+  else if (!have_bases) return sfail(s, RR_ERR_ARG, "rr_sim_attach: this session was made from an index and holds no bases (use rr_sim_attach_device)");
+  else rc = rr_set_references(ctx, ptr.size(), ptr.data(), len.data(), circ.data());
   if (!rc) {
     if (s->error_random) rc = rr_set_error_model(ctx, s->k, 0, nullptr, nullptr, nullptr, nullptr, nullptr);
     else rc = rr_set_error_model(ctx, s->k, s->em_alt_begin.size() - 1, s->em_keys.data(), s->em_alt_begin.data(), s->em_alt_off.data(),
@@ -626,6 +671,13 @@ RR_API int rr_sim_attach(const rr_sim* s_, rr_ctx* ctx) {
   if (!rc) rc = rr_set_glitch(ctx, s->p.glitch_rate, s->p.glitch_size, s->p.glitch_skip);
   if (rc) s->err = std::string("rr_sim_attach: ") + rr_last_error(ctx);
   return rc;
+}
+
+RR_API int rr_sim_attach(const rr_sim* s, rr_ctx* ctx) { return attach(const_cast<rr_sim*>(s), ctx, nullptr); }
+
+RR_API int rr_sim_attach_device(const rr_sim* s, rr_ctx* ctx, const void* device_bases) {
+  if (!device_bases) return RR_ERR_ARG;
+  return attach(const_cast<rr_sim*>(s), ctx, device_bases);
 }
 
 // Fragments::generate_fragment (src/simulate/fragments.rs:72-114); returns the counted length
@@ -643,7 +695,7 @@ static uint64_t feed_fragment(rr_sim* s, bool* ok, uint32_t& type, uint32_t& ref
   {
     bool possible = false;
     for (const Contig& c : s->contigs)
-      if (c.weight > 0.0 && !(length >= c.seq.size() && c.circular)) { possible = true; break; }
+      if (c.weight > 0.0 && !(length >= c.len && c.circular)) { possible = true; break; }
     if (!possible) { *ok = false; s->err = "fragment of " + std::to_string(length) + " bases fits no contig: every selectable contig is circular and shorter (the reference loops forever here; use a shorter --length or add a linear contig)"; return 0; }
   }
   size_t idx;
@@ -651,10 +703,10 @@ static uint64_t feed_fragment(rr_sim* s, bool* ok, uint32_t& type, uint32_t& ref
     strand = g.range_u32(0, 1) == 0 ? RR_PLUS : RR_MINUS;
     idx = s->contig_dist.sample(g);
     const Contig& c = s->contigs[idx];
-    if (!(length >= c.seq.size() && c.circular)) break;  // fragment_is_possible (fragments.rs:117-123)
+    if (!(length >= c.len && c.circular)) break;  // fragment_is_possible (fragments.rs:117-123)
   }
   const Contig& c = s->contigs[idx];
-  const uint64_t rl = c.seq.size();
+  const uint64_t rl = c.len;
   ref_idx = (uint32_t)idx;
   uint64_t b = g.range_u64(0, rl - 1);
   start = b;

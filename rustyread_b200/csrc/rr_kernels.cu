@@ -78,9 +78,8 @@ struct rr_ctx {
   DevBuf d_lcs_tab;
   DevBuf d_q_tab_off, d_q_tab, d_q_dist_off, d_q_scores, d_q_cum, d_q_scale, d_q_unit, d_q_guide;
 
-  // Up to two batches in flight (rr_submit / rr_collect): per-batch state lives in a slot; the big working
-  // arenas (raw / err / cigar) and the per-warp scratch are shared because kernels of consecutive batches are
-  // serialised on the compute stream, while the D2H of batch i (copy stream) overlaps the kernels of batch i+1.
+  // Up to two batches in flight (rr_submit / rr_collect): all per-batch state, arenas and scratch included, lives in a
+  // slot; the D2H of batch i (copy stream) overlaps the kernels of batch i+1 (the other slot's compute stream).
   struct Slot {
     uint64_t n = 0;
     std::vector<rr_desc> descs;
@@ -93,6 +92,12 @@ struct rr_ctx {
     DevBuf d_descs, d_order, d_queue, d_raw_off, d_out_off;
     DevBuf d_raw_len, d_err_len, d_cig_len, d_q_cursor, d_real_id, d_status, d_packed_off, d_totals;
     DevBuf d_seq, d_qual;
+    // every slot has its own compute stream, working arenas and per-warp scratch: the kernels of two batches in flight may
+    // share the GPU (the persistent blocks of the next batch's read kernel move in as the tail of this one's retire)
+    cudaStream_t stream = nullptr;
+    DevBuf d_raw, d_err, d_cig;
+    DevBuf d_sc_rows, d_sc_ops, d_sc_grec, d_sc_gseq;
+    uint64_t sc_grec_alloc = 0, sc_gseq_alloc = 0;  // per-warp capacities the scratch is allocated for
     PinBuf h_seq, h_qual, h_off, h_len, h_id, h_totals, h_status;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
     cudaEvent_t done = nullptr;
@@ -118,9 +123,8 @@ struct rr_ctx {
   cudaStream_t copy_stream = nullptr;
   double initial_slack = 1.5;  // capacity planning slack (rr_debug_set_slack)
   uint64_t n_replans = 0;      // how many times a batch had to be re-planned with more slack
-  DevBuf d_raw, d_err, d_cig;
-  DevBuf d_sc_rows, d_sc_ops, d_sc_grec, d_sc_gseq;
-  uint64_t sc_rows_cap = 32768, sc_ops_cap = 16384, sc_grec_cap = 0, sc_gseq_cap = 0;
+  DevBuf d_sc_rows, d_sc_ops;  // scratch of rr_debug_align
+  uint64_t sc_rows_cap = 32768, sc_ops_cap = 16384;  // per-warp alignment scratch (words / bytes)
 };
 
 // RR_TRACE=1: host-side timeline of the batch pipeline on stderr (developer aid, off by default)
@@ -254,7 +258,9 @@ RR_API int rr_create(int device, rr_ctx** out) {
   for (auto* kern : {rr_read_kernel<EM_RANDOM, 7>, rr_read_kernel<EM_PACKED, 7>, rr_read_kernel<EM_TABLES, 7>,
                      rr_read_kernel<EM_RANDOM, 0>, rr_read_kernel<EM_PACKED, 0>, rr_read_kernel<EM_TABLES, 0>}) {
     CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)READ_KERNEL_SMEM));
-    CK(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    // RR_SMEM_CARVEOUT (developer A/B): percent of the SM's L1 / shared memory array preferred as shared memory
+    static const int carveout = std::getenv("RR_SMEM_CARVEOUT") ? std::atoi(std::getenv("RR_SMEM_CARVEOUT")) : (int)cudaSharedmemCarveoutMaxShared;
+    CK(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, carveout));
   }
   ctx = new rr_ctx();
   ctx->device = device;
@@ -265,6 +271,8 @@ RR_API int rr_create(int device, rr_ctx** out) {
     for (auto& ev : sl.ev) cudaEventCreate(&ev);
     cudaEventCreateWithFlags(&sl.done, cudaEventDisableTiming);
   }
+  ctx->slot[0].stream = ctx->stream;  // rr_upload / rr_run (and rr_stream) work on slot 0
+  if (cudaStreamCreateWithFlags(&ctx->slot[1].stream, cudaStreamNonBlocking) != cudaSuccess) { rr_destroy(ctx); return fail(nullptr, RR_ERR_CUDA, "cudaStreamCreate failed"); }
   if (build_lcs_table(ctx) != RR_OK) {
     g_create_error = "rr_create: " + ctx->err;
     rr_destroy(ctx);
@@ -278,16 +286,18 @@ RR_API void rr_destroy(rr_ctx* ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
+  if (ctx->slot[1].stream) cudaStreamSynchronize(ctx->slot[1].stream);
   cudaStreamSynchronize(ctx->copy_stream);
   DevBuf* bufs[] = {&ctx->d_ref, &ctx->d_ref_off, &ctx->d_ref_circ, &ctx->d_em_index, &ctx->d_em_alt_begin, &ctx->d_em_alt_off,
                     &ctx->d_em_alt_bytes, &ctx->d_em_cum, &ctx->d_em_scale, &ctx->d_em_piece_begin, &ctx->d_em_piece_off, &ctx->d_em_piece_edits,
                     &ctx->d_em_piece_ops, &ctx->d_em_koff, &ctx->d_em_kblob, &ctx->d_em_arec, &ctx->d_adapter, &ctx->d_lcs_tab, &ctx->d_q_tab_off, &ctx->d_q_tab,
-                    &ctx->d_q_dist_off, &ctx->d_q_scores, &ctx->d_q_cum, &ctx->d_q_scale, &ctx->d_q_unit, &ctx->d_q_guide, &ctx->d_raw, &ctx->d_err, &ctx->d_cig,
-                    &ctx->d_sc_rows, &ctx->d_sc_ops, &ctx->d_sc_grec, &ctx->d_sc_gseq};
+                    &ctx->d_q_dist_off, &ctx->d_q_scores, &ctx->d_q_cum, &ctx->d_q_scale, &ctx->d_q_unit, &ctx->d_q_guide,
+                    &ctx->d_sc_rows, &ctx->d_sc_ops};
   for (auto* b : bufs) b->release();
   for (auto& sl : ctx->slot) {
     DevBuf* sb[] = {&sl.d_descs, &sl.d_order, &sl.d_queue, &sl.d_raw_off, &sl.d_out_off, &sl.d_raw_len, &sl.d_err_len, &sl.d_cig_len,
-                    &sl.d_q_cursor, &sl.d_real_id, &sl.d_status, &sl.d_packed_off, &sl.d_totals, &sl.d_seq, &sl.d_qual};
+                    &sl.d_q_cursor, &sl.d_real_id, &sl.d_status, &sl.d_packed_off, &sl.d_totals, &sl.d_seq, &sl.d_qual,
+                    &sl.d_raw, &sl.d_err, &sl.d_cig, &sl.d_sc_rows, &sl.d_sc_ops, &sl.d_sc_grec, &sl.d_sc_gseq};
     for (auto* b : sb) b->release();
     PinBuf* pins[] = {&sl.h_seq, &sl.h_qual, &sl.h_off, &sl.h_len, &sl.h_id, &sl.h_totals, &sl.h_status};
     for (auto* b : pins) b->release();
@@ -300,6 +310,7 @@ RR_API void rr_destroy(rr_ctx* ctx) {
     if (pt.ev) cudaEventDestroy(pt.ev);
   }
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
+  if (ctx->slot[1].stream) cudaStreamDestroy(ctx->slot[1].stream);
   if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
   delete ctx;
 }
@@ -335,6 +346,44 @@ RR_API int rr_set_references(rr_ctx* ctx, uint64_t n, const uint8_t* const* seq,
   ctx->M.ref_circ = ctx->d_ref_circ.as<uint8_t>();
   ctx->M.n_refs = (uint32_t)n;
   ctx->have_refs = true;
+  return RR_OK;
+}
+
+RR_API int rr_set_references_device(rr_ctx* ctx, uint64_t n, const uint64_t* len, const uint8_t* circular, const void* device_bases) {
+  if (!ctx) return RR_ERR_ARG;
+  if (n == 0 || !len || !device_bases) return fail(ctx, RR_ERR_ARG, "rr_set_references_device: no contigs");
+  if (n > 0xffffffffULL) return fail(ctx, RR_ERR_UNSUPPORTED, "rr_set_references_device: too many contigs");
+  CK(cudaSetDevice(ctx->device));
+  cudaPointerAttributes at{};
+  if (cudaPointerGetAttributes(&at, device_bases) != cudaSuccess || (at.type != cudaMemoryTypeDevice && at.type != cudaMemoryTypeManaged) ||
+      at.device != ctx->device) {
+    cudaGetLastError();
+    return fail(ctx, RR_ERR_ARG, "rr_set_references_device: not device memory of this context's GPU");
+  }
+  std::vector<uint64_t> off(n + 1, 0);
+  for (uint64_t i = 0; i < n; ++i) off[i + 1] = off[i] + len[i];
+  ENSURE(ctx->d_ref, std::max<uint64_t>(16, off[n]));
+  if (off[n]) CK(cudaMemcpyAsync(ctx->d_ref.p, device_bases, off[n], cudaMemcpyDeviceToDevice, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  ctx->ref_len.assign(len, len + n);
+  ctx->ref_circ.assign(n, 0);
+  if (circular) for (uint64_t i = 0; i < n; ++i) ctx->ref_circ[i] = circular[i] ? 1 : 0;
+  if (!upload(ctx, ctx->d_ref_off, off) || !upload(ctx, ctx->d_ref_circ, ctx->ref_circ)) return fail(ctx, RR_ERR_CUDA, "rr_set_references_device: upload failed");
+  ctx->M.ref_bytes = ctx->d_ref.as<uint8_t>();
+  ctx->M.ref_off = ctx->d_ref_off.as<uint64_t>();
+  ctx->M.ref_circ = ctx->d_ref_circ.as<uint8_t>();
+  ctx->M.n_refs = (uint32_t)n;
+  ctx->have_refs = true;
+  return RR_OK;
+}
+
+RR_API int rr_references_device(const rr_ctx* ctx, const void** device_bases, uint64_t* bytes) {
+  if (!ctx || !device_bases || !bytes) return RR_ERR_ARG;
+  if (!ctx->have_refs) return RR_ERR_ARG;
+  uint64_t total = 0;
+  for (uint64_t l : ctx->ref_len) total += l;
+  *device_bases = ctx->d_ref.p;
+  *bytes = total;
   return RR_OK;
 }
 
@@ -715,36 +764,31 @@ static int plan(rr_ctx* ctx, Slot& sl) {
   return RR_OK;
 }
 
-// H2D of the plan + (re)allocation of everything the kernels of this batch touch.  Reallocation of a SHARED buffer
-// must not race with kernels of the other slot still in flight: the caller drains the compute stream first when needed.
+// H2D of the plan + (re)allocation of everything the kernels of this batch touch (all of it owned by the slot, which is
+// idle here: its previous batch has been collected).
 static int upload_plan(rr_ctx* ctx, Slot& sl) {
   const uint64_t n = sl.n;
   uint32_t want_blocks = (uint32_t)std::min<uint64_t>((uint64_t)ctx->n_sm * RR_BLOCKS_PER_SM, (n + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK);
   sl.read_grid = std::max<uint32_t>(1, want_blocks);  // persistent grid: 4 blocks of 8 warps per SM, fewer if the batch is small
   const uint64_t n_warps = (uint64_t)ctx->n_sm * RR_BLOCKS_PER_SM * WARPS_PER_BLOCK;
-  const uint64_t grec = std::max(ctx->sc_grec_cap, sl.sc_grec_cap), gseq = std::max(ctx->sc_gseq_cap, sl.sc_gseq_cap);
-  const bool grow = sl.h_raw_off[n] + 16 > ctx->d_raw.cap || sl.h_out_off[n] + 16 > ctx->d_err.cap || sl.h_out_off[n] + 16 > ctx->d_cig.cap ||
-                    n_warps * ctx->sc_rows_cap * 8 > ctx->d_sc_rows.cap || n_warps * ctx->sc_ops_cap > ctx->d_sc_ops.cap ||
-                    n_warps * grec * sizeof(GlitchRec) > ctx->d_sc_grec.cap || n_warps * gseq > ctx->d_sc_gseq.cap;
-  if (grow) CK(cudaStreamSynchronize(ctx->stream));  // another batch may still be using the shared arenas
-  ctx->sc_grec_cap = grec;
-  ctx->sc_gseq_cap = gseq;
-  ENSURE(ctx->d_raw, sl.h_raw_off[n] + 16);
-  ENSURE(ctx->d_err, sl.h_out_off[n] + 16);
-  ENSURE(ctx->d_cig, sl.h_out_off[n] + 16);
-  ENSURE(ctx->d_sc_rows, n_warps * ctx->sc_rows_cap * 8);
-  ENSURE(ctx->d_sc_ops, n_warps * ctx->sc_ops_cap);
-  ENSURE(ctx->d_sc_grec, n_warps * ctx->sc_grec_cap * sizeof(GlitchRec));
-  ENSURE(ctx->d_sc_gseq, n_warps * ctx->sc_gseq_cap);
+  sl.sc_grec_alloc = std::max(sl.sc_grec_alloc, sl.sc_grec_cap);
+  sl.sc_gseq_alloc = std::max(sl.sc_gseq_alloc, sl.sc_gseq_cap);
+  ENSURE(sl.d_raw, sl.h_raw_off[n] + 16);
+  ENSURE(sl.d_err, sl.h_out_off[n] + 16);
+  ENSURE(sl.d_cig, sl.h_out_off[n] + 16);
+  ENSURE(sl.d_sc_rows, n_warps * ctx->sc_rows_cap * 8);
+  ENSURE(sl.d_sc_ops, n_warps * ctx->sc_ops_cap);
+  ENSURE(sl.d_sc_grec, n_warps * sl.sc_grec_alloc * sizeof(GlitchRec));
+  ENSURE(sl.d_sc_gseq, n_warps * sl.sc_gseq_alloc);
   ENSURE(sl.d_raw_off, (n + 1) * 8);
   ENSURE(sl.d_out_off, (n + 1) * 8);
   ENSURE(sl.d_order, n * 4);
   // worst-case packed size (capacities), so that no host round trip is needed between the kernels of a batch
   ENSURE(sl.d_seq, sl.h_out_off[n] + 16);
   ENSURE(sl.d_qual, sl.h_out_off[n] + 16);
-  CK(cudaMemcpyAsync(sl.d_raw_off.p, sl.h_raw_off.data(), (n + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
-  CK(cudaMemcpyAsync(sl.d_out_off.p, sl.h_out_off.data(), (n + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
-  CK(cudaMemcpyAsync(sl.d_order.p, sl.h_order.data(), n * 4, cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemcpyAsync(sl.d_raw_off.p, sl.h_raw_off.data(), (n + 1) * 8, cudaMemcpyHostToDevice, sl.stream));
+  CK(cudaMemcpyAsync(sl.d_out_off.p, sl.h_out_off.data(), (n + 1) * 8, cudaMemcpyHostToDevice, sl.stream));
+  CK(cudaMemcpyAsync(sl.d_order.p, sl.h_order.data(), n * 4, cudaMemcpyHostToDevice, sl.stream));
   return RR_OK;
 }
 
@@ -773,7 +817,7 @@ static int prepare(rr_ctx* ctx, Slot& sl, uint64_t n, const rr_desc* descs) {
   ENSURE(sl.d_totals, 32);
   ENSURE(sl.h_totals, 32);
   ENSURE(sl.h_status, n * 4);
-  CK(cudaMemcpyAsync(sl.d_descs.p, sl.descs.data(), n * sizeof(rr_desc), cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemcpyAsync(sl.d_descs.p, sl.descs.data(), n * sizeof(rr_desc), cudaMemcpyHostToDevice, sl.stream));
   rc = upload_plan(ctx, sl);
   if (rc) return rc;
   sl.prepared = true;
@@ -795,30 +839,30 @@ static int enqueue(rr_ctx* ctx, Slot& sl) {
   P.fast_warps = g_fast_warps;
   P.raw_off = sl.d_raw_off.as<uint64_t>();
   P.out_off = sl.d_out_off.as<uint64_t>();
-  P.raw = ctx->d_raw.as<uint8_t>();
-  P.err = ctx->d_err.as<uint8_t>();
-  P.cig = ctx->d_cig.as<uint8_t>();
+  P.raw = sl.d_raw.as<uint8_t>();
+  P.err = sl.d_err.as<uint8_t>();
+  P.cig = sl.d_cig.as<uint8_t>();
   P.raw_len = sl.d_raw_len.as<uint64_t>();
   P.err_len = sl.d_err_len.as<uint64_t>();
   P.cig_len = sl.d_cig_len.as<uint64_t>();
   P.q_cursor = sl.d_q_cursor.as<uint64_t>();
   P.real_id = sl.d_real_id.as<double>();
   P.status = sl.d_status.as<uint32_t>();
-  P.sc_rows = ctx->d_sc_rows.as<uint64_t>();  P.sc_rows_cap = ctx->sc_rows_cap;
-  P.sc_ops = ctx->d_sc_ops.as<uint8_t>();     P.sc_ops_cap = ctx->sc_ops_cap;
-  P.sc_grec = ctx->d_sc_grec.as<GlitchRec>(); P.sc_grec_cap = ctx->sc_grec_cap;
-  P.sc_gseq = ctx->d_sc_gseq.as<uint8_t>();   P.sc_gseq_cap = ctx->sc_gseq_cap;
+  P.sc_rows = sl.d_sc_rows.as<uint64_t>();  P.sc_rows_cap = ctx->sc_rows_cap;
+  P.sc_ops = sl.d_sc_ops.as<uint8_t>();     P.sc_ops_cap = ctx->sc_ops_cap;
+  P.sc_grec = sl.d_sc_grec.as<GlitchRec>(); P.sc_grec_cap = sl.sc_grec_alloc;
+  P.sc_gseq = sl.d_sc_gseq.as<uint8_t>();   P.sc_gseq_cap = sl.sc_gseq_alloc;
 
-  CK(cudaMemsetAsync(sl.d_queue.p, 0, 16, ctx->stream));
-  CK(cudaEventRecord(sl.ev[0], ctx->stream));
+  CK(cudaMemsetAsync(sl.d_queue.p, 0, 16, sl.stream));
+  CK(cudaEventRecord(sl.ev[0], sl.stream));
   const bool k7 = ctx->M.k == 7;
   auto* read_kernel = !ctx->M.em_index ? (k7 ? rr_read_kernel<EM_RANDOM, 7> : rr_read_kernel<EM_RANDOM, 0>)
                       : ctx->M.em_koff ? (k7 ? rr_read_kernel<EM_PACKED, 7> : rr_read_kernel<EM_PACKED, 0>)
                                        : (k7 ? rr_read_kernel<EM_TABLES, 7> : rr_read_kernel<EM_TABLES, 0>);
-  read_kernel<<<sl.read_grid, WARPS_PER_BLOCK * 32, READ_KERNEL_SMEM, ctx->stream>>>(P);
+  read_kernel<<<sl.read_grid, WARPS_PER_BLOCK * 32, READ_KERNEL_SMEM, sl.stream>>>(P);
   CK(cudaGetLastError());
-  CK(cudaEventRecord(sl.ev[1], ctx->stream));
-  rr_scan_kernel<<<1, 1024, 0, ctx->stream>>>(sl.d_err_len.as<uint64_t>(), sl.d_status.as<uint32_t>(), n, ctx->M.k,
+  CK(cudaEventRecord(sl.ev[1], sl.stream));
+  rr_scan_kernel<<<1, 1024, 0, sl.stream>>>(sl.d_err_len.as<uint64_t>(), sl.d_status.as<uint32_t>(), n, ctx->M.k,
                                               sl.d_packed_off.as<uint64_t>(), sl.d_totals.as<uint64_t>());
   CK(cudaGetLastError());
   QscoreKernelParams QP{};
@@ -839,16 +883,16 @@ static int enqueue(rr_ctx* ctx, Slot& sl) {
   QP.seq = sl.d_seq.as<uint8_t>();
   uint32_t qgrid = (uint32_t)std::min<uint64_t>((uint64_t)ctx->n_sm * (2048 / Q_THREADS), n);  // every resident slot of the SMs, dynamic queue
   const bool q_k1 = ctx->Q.max_k == 1, q_cached = ctx->Q.n_dist <= QD_CACHE && ctx->Q.n_scores <= QS_CACHE;
-  if (q_k1 && q_cached) rr_qscore_kernel<true, true><<<qgrid, Q_THREADS, 0, ctx->stream>>>(QP);
-  else if (q_k1) rr_qscore_kernel<true, false><<<qgrid, Q_THREADS, 0, ctx->stream>>>(QP);
-  else if (q_cached) rr_qscore_kernel<false, true><<<qgrid, Q_THREADS, 0, ctx->stream>>>(QP);
-  else rr_qscore_kernel<false, false><<<qgrid, Q_THREADS, 0, ctx->stream>>>(QP);
+  if (q_k1 && q_cached) rr_qscore_kernel<true, true><<<qgrid, Q_THREADS, 0, sl.stream>>>(QP);
+  else if (q_k1) rr_qscore_kernel<true, false><<<qgrid, Q_THREADS, 0, sl.stream>>>(QP);
+  else if (q_cached) rr_qscore_kernel<false, true><<<qgrid, Q_THREADS, 0, sl.stream>>>(QP);
+  else rr_qscore_kernel<false, false><<<qgrid, Q_THREADS, 0, sl.stream>>>(QP);
   CK(cudaGetLastError());
-  CK(cudaEventRecord(sl.ev[2], ctx->stream));
-  CK(cudaEventRecord(sl.ev[3], ctx->stream));
-  CK(cudaMemcpyAsync(sl.h_totals.p, sl.d_totals.p, 24, cudaMemcpyDeviceToHost, ctx->stream));
-  CK(cudaMemcpyAsync(sl.h_status.p, sl.d_status.p, (size_t)n * 4, cudaMemcpyDeviceToHost, ctx->stream));
-  CK(cudaEventRecord(sl.done, ctx->stream));
+  CK(cudaEventRecord(sl.ev[2], sl.stream));
+  CK(cudaEventRecord(sl.ev[3], sl.stream));
+  CK(cudaMemcpyAsync(sl.h_totals.p, sl.d_totals.p, 24, cudaMemcpyDeviceToHost, sl.stream));
+  CK(cudaMemcpyAsync(sl.h_status.p, sl.d_status.p, (size_t)n * 4, cudaMemcpyDeviceToHost, sl.stream));
+  CK(cudaEventRecord(sl.done, sl.stream));
   ctx->launches += 3;
   sl.enqueued = true;
   return RR_OK;
@@ -939,7 +983,7 @@ RR_API int rr_upload(rr_ctx* ctx, uint64_t n, const rr_desc* descs) {
   if (rc) return rc;
   rc = prepare(ctx, ctx->slot[0], n, descs);
   if (rc) return rc;
-  CK(cudaStreamSynchronize(ctx->stream));
+  CK(cudaStreamSynchronize(ctx->slot[0].stream));
   return RR_OK;
 }
 
@@ -1228,7 +1272,7 @@ RR_API int rr_debug_fetch(rr_ctx* ctx, uint64_t i, int which, uint8_t* out, uint
   const DevBuf& lens = which == 0 ? sl.d_raw_len : sl.d_cig_len;
   CK(cudaMemcpy(&l, lens.as<uint64_t>() + i, 8, cudaMemcpyDeviceToHost));
   if (l > cap) return fail(ctx, RR_ERR_ARG, "rr_debug_fetch: buffer too small");
-  const uint8_t* src = which == 0 ? ctx->d_raw.as<uint8_t>() + sl.h_raw_off[i] : ctx->d_cig.as<uint8_t>() + sl.h_out_off[i];
+  const uint8_t* src = which == 0 ? sl.d_raw.as<uint8_t>() + sl.h_raw_off[i] : sl.d_cig.as<uint8_t>() + sl.h_out_off[i];
   if (l) CK(cudaMemcpy(out, src, l, cudaMemcpyDeviceToHost));
   *len = l;
   return RR_OK;

@@ -117,9 +117,11 @@ def shard_bounds(descs, world):
 class DeviceGenerator:
     """generate_fn backed by the CUDA library: descs -> (offsets, lengths, seq, qual, real_identity)."""
 
-    def __init__(self, sim, device=0):
-        self.ctx = capi.Context(device)
-        sim.attach(self.ctx)
+    def __init__(self, sim, device=0, ctx=None):
+        if ctx is None:
+            ctx = capi.Context(device)
+            sim.attach(ctx)
+        self.ctx = ctx  # a context that already holds the session's references and models
 
     def batch(self, descs):
         """The library-owned batch (pinned arenas, valid until the next call); None for an empty shard."""
@@ -156,6 +158,40 @@ def _recv(dist, dtypes, src):
             dist.recv(t, src)
         out.append(t.numpy().view(dt))
     return out
+
+
+class _DeviceBytes:
+    """A device address as something torch.as_tensor understands (no copy)."""
+
+    def __init__(self, ptr, n):
+        self.__cuda_array_interface__ = {"shape": (n,), "typestr": "|u1", "data": (ptr, False), "version": 2}
+
+
+def shared_reference_context(sim, dist, rank, device, n_bytes):
+    """One rank of a box read and parsed the FASTA; its device copy of the reference goes to the GPUs of the other ranks
+    over NVLink (one NCCL broadcast of the concatenated contigs) instead of every rank parsing the file and uploading it
+    over PCIe.  This is the only collective that moves reference or read data, and it runs once, before the first batch.
+    Returns a device context with references and models attached."""
+    import torch
+
+    torch.cuda.set_device(device)
+    ctx = capi.Context(device)
+    group = dist.new_group(backend="nccl")
+    if rank == 0:
+        sim.attach(ctx)
+        ptr, n = ctx.references_device()
+        if n != n_bytes:
+            raise RuntimeError("reference arena holds %d bytes, index says %d" % (n, n_bytes))
+        t = torch.as_tensor(_DeviceBytes(ptr, n), device="cuda:%d" % device)
+    else:
+        t = torch.empty(n_bytes, dtype=torch.uint8, device="cuda:%d" % device)
+    dist.broadcast(t, 0, group=group)
+    torch.cuda.synchronize()
+    if rank != 0:
+        sim.attach(ctx, device_bases=t.data_ptr())
+    del t
+    dist.destroy_process_group(group)
+    return ctx
 
 
 def piece_bounds(descs, world, chunk_bases):
@@ -317,8 +353,11 @@ def _simulate_single_gpu(sim, total, limit, output, device, chunk_bases):
 
 
 def simulate(fasta, quantity, output, generate_factory=None, dist=None, rank=0, world=1, device=0, chunk_bases=1_000_000_000, output_path=None,
-             **flags):
+             share_reference=False, **flags):
     """Run `rustyread simulate`.  `output` is a binary file object (only used on rank 0).  Returns (reads, bases).
+
+    share_reference (world > 1, device path): only rank 0 needs `fasta`; the other ranks build their session from the contig
+    index rank 0 broadcasts and receive the bases device to device (shared_reference_context).
 
     world > 1 with `output_path` (a regular file every rank can open): every rank formats the records of its own shard
     and writes them at their final offset with pwrite (parallel writer); otherwise the shards travel to rank 0, the
@@ -331,13 +370,33 @@ def simulate(fasta, quantity, output, generate_factory=None, dist=None, rank=0, 
     def model_text(v, kind, builtins):
         return v if v in builtins else read_maybe_compressed(found_model(v, kind))
 
-    sim = capi.Simulation(fasta, seed=f["seed"], length=parse_duo(f["length"]), identity=parse_trio(f["identity"]),
-                          start_adapter=parse_duo(f["start_adapter"]), end_adapter=parse_duo(f["end_adapter"]),
-                          start_adapter_seq=f["start_adapter_seq"], end_adapter_seq=f["end_adapter_seq"],
-                          junk_reads=f["junk_reads"], random_reads=f["random_reads"], chimera=f["chimera"],
-                          glitches=parse_trio(f["glitches"]), small_plasmid_bias=f["small_plasmid_bias"],
-                          error_model=model_text(f["error_model"], "error", ("random",)),
-                          qscore_model=model_text(f["qscore_model"], "qscore", ("random", "ideal")))
+    kw = dict(seed=f["seed"], length=parse_duo(f["length"]), identity=parse_trio(f["identity"]),
+              start_adapter=parse_duo(f["start_adapter"]), end_adapter=parse_duo(f["end_adapter"]),
+              start_adapter_seq=f["start_adapter_seq"], end_adapter_seq=f["end_adapter_seq"],
+              junk_reads=f["junk_reads"], random_reads=f["random_reads"], chimera=f["chimera"],
+              glitches=parse_trio(f["glitches"]), small_plasmid_bias=f["small_plasmid_bias"],
+              error_model=model_text(f["error_model"], "error", ("random",)),
+              qscore_model=model_text(f["qscore_model"], "qscore", ("random", "ideal")))
+    share = bool(share_reference) and world > 1 and generate_factory is None
+    if share:
+        # rank 0 parses; everybody else gets the contig index (ids, lengths, circular flags, header weights): the serial
+        # feeder and the writer need nothing else of the reference, and main_rng is drawn from in the same order
+        box = [None]
+        if rank == 0:
+            try:
+                sim = capi.Simulation(fasta, **kw)
+                box = [sim.contig_index()]
+            except Exception as e:  # the other ranks must not wait for an index that never comes
+                box = [e]
+        dist.broadcast_object_list(box, 0)
+        if isinstance(box[0], Exception):
+            raise box[0]
+        if rank != 0:
+            sim = capi.Simulation(None, index=box[0], **kw)
+        shared_ctx = shared_reference_context(sim, dist, rank, device, sum(c[1] for c in box[0]))
+        generate_factory = lambda s: DeviceGenerator(s, device, ctx=shared_ctx)
+    else:
+        sim = capi.Simulation(fasta, **kw)
     total = sim.quantity(quantity)
     limit = sim.quantity(f["number_base_store"]) if f["number_base_store"] else total
     if world == 1 and generate_factory is None:

@@ -629,10 +629,12 @@ def test_capacity_overflow_is_replanned_not_truncated(orc):
     ctx.close()
 
 
-@pytest.mark.parametrize("mode", ["parallel", "parallel-rounds", "single"])
+@pytest.mark.parametrize("mode", ["parallel", "parallel-rounds", "single", "every-rank-parses"])
 def test_two_gpu_cli_matches_oracle(orc, rr, tmp_path, mode):
     """torchrun with 2 ranks (one process per GPU): sharded generation; FASTQ == the oracle's simulate() with the parallel
-    writer (every rank streams its pieces to their final offsets; one or several rounds per batch) and with the single writer."""
+    writer (every rank streams its pieces to their final offsets; one or several rounds per batch) and with the single writer.
+    Rank 1 gets the reference from rank 0's GPU (contig index + one NCCL broadcast) except in the last mode, where it parses the
+    FASTA itself."""
     import os
     import subprocess
     import sys
@@ -651,6 +653,8 @@ def test_two_gpu_cli_matches_oracle(orc, rr, tmp_path, mode):
         env["RUSTYREAD_B200_SINGLE_WRITER"] = "1"
     if mode == "parallel-rounds":
         env["RUSTYREAD_B200_CHUNK_BASES"] = "90000"
+    if mode == "every-rank-parses":
+        env["RUSTYREAD_B200_NO_SHARED_REFERENCE"] = "1"
     r = subprocess.run(cmd, capture_output=True, text=True, cwd=helpers.ROOT, timeout=900, env=env)
     assert r.returncode == 0, r.stderr[-3000:]
     text, stats = orc.simulate(dict(seed=21, quantity="12x", number_base_store="700K", threads=8), fasta, capture=True)

@@ -244,3 +244,35 @@ def test_loader_rejects_what_the_reference_rejects(rr, orc):
         capi.Simulation(b"")
     with pytest.raises(rr.RRError):
         capi.Simulation(fasta, qscore_model="overall;3;1:0.5,\n=;1;x:0.5,\n")
+
+
+def test_session_from_contig_index_is_the_same_session(orc, rr):
+    """rr_sim_create_indexed (a rank that receives the bases device to device): same main_rng schedule, same work items and
+    the same FASTQ text as the session made from the FASTA itself."""
+    import rustyread_b200.capi as capi
+
+    fasta = helpers.random_fasta(orc, [40_000, 3_000, 9_000], circular={1}, depth={2: "2.5"})
+    kw = dict(seed=11, length=(1500, 1300), junk_reads=5, random_reads=5, chimera=10, glitches=(800, 25, 25))
+    a = capi.Simulation(fasta, **kw)
+    idx = a.contig_index()
+    assert [c[1] for c in idx] == [40_000, 3_000, 9_000] and [c[2] for c in idx] == [False, True, False]
+    assert idx[2][3] == 2.5 * 9_000 and idx[0][0] == "contig_0"
+    b = capi.Simulation(None, index=idx, **kw)
+    assert b.genome_length == a.genome_length and a.rng_words() == b.rng_words()
+    assert [(r["id"], r["circular"], r["weight"]) for r in a.refs()] == [(r["id"], r["circular"], r["weight"]) for r in b.refs()]
+    rs = np.random.RandomState(4)
+    for _ in range(2):
+        da, db = a.feed(150_000), b.feed(150_000)
+        assert len(da) > 20 and np.array_equal(da, db)
+        # any results will do for the writer: the text depends on the session only through descriptors, ids and main_rng
+        lens = (rs.randint(10, 400, size=len(da))).astype(np.uint64)
+        off = np.concatenate([[0], np.cumsum((lens + 15) // 16 * 16)]).astype(np.uint64)
+        seq = rs.choice(np.frombuffer(b"ACGT", np.uint8), size=int(off[-1]))
+        qual = rs.randint(34, 70, size=int(off[-1])).astype(np.uint8)
+        ident = rs.uniform(80, 99, size=len(da))
+        ta = a.fastq(capi.batch_struct_from_arrays(off, lens, seq, qual, ident, a.k))
+        tb = b.fastq(capi.batch_struct_from_arrays(off, lens, seq, qual, ident, b.k))
+        assert ta == tb and ta[1] > 10
+        assert a.rng_words() == b.rng_words()
+    with pytest.raises(capi.RRError):
+        capi.Simulation(None, index=[], **kw)
