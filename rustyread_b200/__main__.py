@@ -44,7 +44,11 @@ def main(argv=None):
         import torch
 
         share = torch.cuda.is_available() and dist.is_nccl_available()
+    if os.environ.get("RUSTYREAD_B200_TIMING"):
+        print("rustyread_b200 timing rank %d: imports + process group %.3f s" % (rank, time.perf_counter() - t_start), file=sys.stderr, flush=True)
     fasta = sim_mod.read_maybe_compressed(a.reference) if (rank == 0 or not share) else None  # niffler: plain, gz, bz2 or xz by magic number
+    if os.environ.get("RUSTYREAD_B200_TIMING"):
+        print("rustyread_b200 timing rank %d: reference read at %.3f s" % (rank, time.perf_counter() - t_start), file=sys.stderr, flush=True)
     out = (open(a.output, "wb") if a.output else sys.stdout.buffer) if rank == 0 else None
     flags = {k: getattr(a, k) for k in d}
     chunk = int(os.environ.get("RUSTYREAD_B200_CHUNK_BASES", "1000000000"))  # device chunk size inside one reference batch

@@ -378,6 +378,20 @@ def simulate(fasta, quantity, output, generate_factory=None, dist=None, rank=0, 
               error_model=model_text(f["error_model"], "error", ("random",)),
               qscore_model=model_text(f["qscore_model"], "qscore", ("random", "ideal")))
     share = bool(share_reference) and world > 1 and generate_factory is None
+    import os
+    import sys
+    import time
+
+    timing = os.environ.get("RUSTYREAD_B200_TIMING")  # developer aid: where the set-up time of this rank goes (stderr)
+    t_setup = time.perf_counter()
+
+    def lap(what):
+        nonlocal t_setup
+        if timing:
+            now = time.perf_counter()
+            print("rustyread_b200 timing rank %d: %s %.3f s" % (rank, what, now - t_setup), file=sys.stderr, flush=True)
+            t_setup = now
+
     if share:
         # rank 0 parses; everybody else gets the contig index (ids, lengths, circular flags, header weights): the serial
         # feeder and the writer need nothing else of the reference, and main_rng is drawn from in the same order
@@ -388,15 +402,19 @@ def simulate(fasta, quantity, output, generate_factory=None, dist=None, rank=0, 
                 box = [sim.contig_index()]
             except Exception as e:  # the other ranks must not wait for an index that never comes
                 box = [e]
+        lap("parse reference + models (rank 0)")
         dist.broadcast_object_list(box, 0)
         if isinstance(box[0], Exception):
             raise box[0]
         if rank != 0:
             sim = capi.Simulation(None, index=box[0], **kw)
+        lap("contig index received, session ready")
         shared_ctx = shared_reference_context(sim, dist, rank, device, sum(c[1] for c in box[0]))
+        lap("device context + reference broadcast")
         generate_factory = lambda s: DeviceGenerator(s, device, ctx=shared_ctx)
     else:
         sim = capi.Simulation(fasta, **kw)
+        lap("parse reference + models")
     total = sim.quantity(quantity)
     limit = sim.quantity(f["number_base_store"]) if f["number_base_store"] else total
     if world == 1 and generate_factory is None:

@@ -27,7 +27,7 @@ def md5(path):
     return h.hexdigest()
 
 
-for ranks in (n, 1):
+for ranks in ((n, 1) if not os.environ.get("RR_ONLY_N") else (n,)):
     out = "/dev/shm/rr_out_%d.fastq" % ranks
     base = [sys.executable, "-m", "rustyread_b200", "-v", "simulate", "--reference", ref, "--quantity", q, "--seed", "42", "--error_model", "random",
             "--qscore_model", "random", "--output", out]
@@ -38,7 +38,7 @@ for ranks in (n, 1):
     dt = time.time() - t
     lines = r.stderr.strip().split("\n")
     wrote = [l for l in lines if l.startswith("wrote")]
-    run = {"rc": r.returncode, "wall_s": dt, "timing": [l for l in lines if "timing" in l][:3]}
+    run = {"rc": r.returncode, "wall_s": dt, "timing": sorted(l for l in lines if "timing" in l and ("rank 0" in l or "rank 1:" in l or "rank 1 " in l or "timing (s)" in l))}
     if r.returncode == 0 and wrote:
         run["reads"], run["bases"] = int(wrote[-1].split()[1]), int(wrote[-1].split()[-2])
         run["gbases_per_s_whole_process"] = run["bases"] / dt / 1e9
@@ -50,7 +50,7 @@ for ranks in (n, 1):
         os.remove(out)
     res["runs"]["%d_gpu" % ranks] = run
     print(json.dumps({("%d_gpu" % ranks): run}), flush=True)
-a, b = res["runs"]["%d_gpu" % n], res["runs"]["1_gpu"]
+a, b = res["runs"]["%d_gpu" % n], res["runs"].get("1_gpu", {"md5": os.environ.get("RR_EXPECT_MD5")})
 res["identical"] = bool(a.get("md5") and a.get("md5") == b.get("md5"))
 os.remove(ref)
 print(json.dumps(res, indent=1))
