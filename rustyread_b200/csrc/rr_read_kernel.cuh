@@ -59,6 +59,38 @@ __device__ __forceinline__ void warp_copy_vec(uint8_t* dst, const uint8_t* src, 
   if (done + (uint64_t)lane < n) dst[done + lane] = src[done + lane];  // tail: fewer than 16 bytes
 }
 
+// Warp copy of a reverse-strand slice: dst[i] = complement(ref[top - i]) for i < n (`revcomp` indexed with forward
+// coordinates, src/simulate/mod.rs:327-338).  Four output bytes per lane and step: two aligned 32-bit loads + a funnel shift
+// fetch the four source bytes, one byte permute reverses them, and the complement of A / C / G / T is bit arithmetic
+// ('A' 0x41 ^ 'T' 0x54 = 0x15, 'C' 0x43 ^ 'G' 0x47 = 0x04; bit 1 tells the pairs apart); a word that holds any other byte
+// (N, IUPAC codes, lower case) goes through complement() byte by byte.  Reads up to 3 bytes around the slice (the
+// reference arena is allocated with slack; its base is aligned).
+__device__ __forceinline__ void warp_copy_revcomp(uint8_t* dst, const uint8_t* ref, uint64_t top, uint64_t n, int lane) {
+  const uint64_t head = min(n, (uint64_t)((4u - (uint32_t)((uintptr_t)dst & 3u)) & 3u));
+  if ((uint64_t)lane < head) dst[lane] = complement(ref[top - lane]);
+  const uint64_t nw = (n - head) >> 2;
+  uint32_t* dw = reinterpret_cast<uint32_t*>(dst + head);
+  for (uint64_t j = lane; j < nw; j += 32) {
+    const uint8_t* lo = ref + (top - head - 4 * j - 3);  // lowest address of the four source bytes
+    const uint32_t sh = (uint32_t)((uintptr_t)lo & 3u) * 8u;
+    const uint32_t* la = reinterpret_cast<const uint32_t*>(lo - (sh >> 3));
+    const uint32_t v = __funnelshift_r(la[0], sh ? la[1] : 0u, sh);
+    uint32_t w = __byte_perm(v, 0, 0x0123);  // byte i of w = source byte top - head - 4j - i
+    const uint32_t y = w ^ 0x41414141u, b0 = y & 0x01010101u;  // the test of raw_is_acgt
+    if ((y & 0xE8E8E8E8u) | (b0 ^ ((y >> 4) & 0x01010101u)) | (b0 ^ ((y >> 2) & ~(y >> 1) & 0x01010101u))) {
+      uint32_t r = 0;
+#pragma unroll 1
+      for (int x = 0; x < 4; ++x) r |= (uint32_t)complement((uint8_t)(w >> (8 * x))) << (8 * x);
+      w = r;
+    } else {
+      w ^= 0x15151515u ^ (((w >> 1) & 0x01010101u) * 0x11u);
+    }
+    dw[j] = w;
+  }
+  const uint64_t done = head + (nw << 2);
+  if (done + (uint64_t)lane < n) dst[done + lane] = complement(ref[top - done - lane]);  // fewer than 4 bytes
+}
+
 // Adapter::get_start / get_end (src/model/adapter.rs:64-93): Bernoulli(rate), then a Beta-distributed
 // prefix of the adapter.  Returns the number of bytes appended.
 __device__ __forceinline__ uint32_t add_adapter(WarpRng& rng, const DeviceModels& M, bool end_side, uint8_t* dst, int lane) {
@@ -103,8 +135,8 @@ __device__ __forceinline__ uint64_t add_fragment(WarpRng& rng, const DeviceModel
     warp_copy_vec(dst, ref + start, n1, lane);
     if (n2) warp_copy_vec(dst + n1, ref, n2, lane);
   } else {
-    for (uint64_t i = lane; i < n1; i += 32) dst[i] = complement(ref[rl - 1 - (start + i)]);
-    for (uint64_t i = lane; i < n2; i += 32) dst[n1 + i] = complement(ref[rl - 1 - i]);
+    warp_copy_revcomp(dst, ref, rl - 1 - start, n1, lane);
+    if (n2) warp_copy_revcomp(dst + n1, ref, rl - 1, n2, lane);
   }
   return n1 + n2;
 }

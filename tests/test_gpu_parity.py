@@ -325,6 +325,48 @@ def test_table_alternatives_longer_than_a_warp_and_other_k(orc, k):
     ctx.close()
 
 
+def _packed_edge_model(k, seed=9):
+    """A model that fits the packed records (k <= 7, alternatives <= 15 bytes) and exercises their edges: alternatives of
+    10..15 unrelated bases (more than 16 ops against the key: the record's entry is invalid and the piece is aligned like any
+    other merge), empty and one-base alternatives, keys with more than 32 alternatives (a second chunk of partial sums), and
+    k-mers that are missing from the table."""
+    rnd = random.Random(seed)
+    lines = []
+    for code in range(4 ** k):
+        if rnd.random() < 0.2:
+            continue  # not in the table: random_error
+        kmer = "".join("ACGT"[(code >> (2 * (k - 1 - i))) & 3] for i in range(k))
+        alts = []
+        na = rnd.choice([1, 2, 3, 5, 40])
+        for _ in range(na):
+            r = rnd.random()
+            if r < 0.25:
+                a = "".join(rnd.choice("ACGT") for _ in range(rnd.randint(10, 15)))
+            elif r < 0.35:
+                a = "".join(rnd.choice("ACGT") for _ in range(rnd.randint(0, 1)))
+            elif r < 0.5:
+                a = kmer + "".join(rnd.choice("ACGT") for _ in range(rnd.randint(1, 15 - k)))
+            else:
+                a = list(kmer)
+                a[rnd.randrange(k)] = rnd.choice("ACGT")
+                if rnd.random() < 0.5:
+                    a.insert(rnd.randrange(k), rnd.choice("ACGT"))
+                else:
+                    del a[rnd.randrange(len(a))]
+                a = "".join(a)
+            alts.append("%s,%s" % (a, repr(round(0.9 / na, 6))))
+        lines.append("%s,0.05;%s;" % (kmer, ";".join(alts)))
+    return "\n".join(lines) + "\n"
+
+
+@pytest.mark.parametrize("k", [4, 7])
+def test_packed_error_model_edges(orc, k):
+    fasta = helpers.random_fasta(orc, [150_000])
+    spec = dict(error_model=_packed_edge_model(k), length=(4000.0, 3000.0), identity=(78.0, 95.0, 6.0), glitch=(900.0, 30.0, 30.0))
+    _, ctx, batch, n = _run_pair(orc, fasta, spec, 700_000)
+    ctx.close()
+
+
 def test_reference_with_bytes_outside_acgt(orc):
     # N runs, IUPAC codes and lower case pass through untouched (src/references.rs:162-166); k-mers that contain them miss the
     # error-model table and alignments that meet them leave the register aligner for the general one
