@@ -73,7 +73,7 @@ struct rr_ctx {
   DevBuf d_ref, d_ref_off, d_ref_circ;
   DevBuf d_em_index, d_em_alt_begin, d_em_alt_off, d_em_alt_bytes, d_em_cum, d_em_scale;
   DevBuf d_em_piece_begin, d_em_piece_off, d_em_piece_edits, d_em_piece_ops;
-  DevBuf d_em_koff, d_em_kblob, d_em_arec;
+  DevBuf d_em_kblob, d_em_arec;
   DevBuf d_adapter;
   DevBuf d_lcs_tab;
   DevBuf d_q_tab_off, d_q_tab, d_q_dist_off, d_q_scores, d_q_cum, d_q_scale, d_q_unit, d_q_guide;
@@ -297,7 +297,7 @@ RR_API void rr_destroy(rr_ctx* ctx) {
   cudaStreamSynchronize(ctx->copy_stream);
   DevBuf* bufs[] = {&ctx->d_ref, &ctx->d_ref_off, &ctx->d_ref_circ, &ctx->d_em_index, &ctx->d_em_alt_begin, &ctx->d_em_alt_off,
                     &ctx->d_em_alt_bytes, &ctx->d_em_cum, &ctx->d_em_scale, &ctx->d_em_piece_begin, &ctx->d_em_piece_off, &ctx->d_em_piece_edits,
-                    &ctx->d_em_piece_ops, &ctx->d_em_koff, &ctx->d_em_kblob, &ctx->d_em_arec, &ctx->d_adapter, &ctx->d_lcs_tab, &ctx->d_q_tab_off, &ctx->d_q_tab,
+                    &ctx->d_em_piece_ops, &ctx->d_em_kblob, &ctx->d_em_arec, &ctx->d_adapter, &ctx->d_lcs_tab, &ctx->d_q_tab_off, &ctx->d_q_tab,
                     &ctx->d_q_dist_off, &ctx->d_q_scores, &ctx->d_q_cum, &ctx->d_q_scale, &ctx->d_q_unit, &ctx->d_q_guide,
                     &ctx->d_sc_rows, &ctx->d_sc_ops};
   for (auto* b : bufs) b->release();
@@ -433,7 +433,7 @@ RR_API int rr_set_error_model(rr_ctx* ctx, uint32_t k, uint64_t n_keys, const ui
   ctx->M.em_alts_acgt = 1;
   if (n_keys == 0) {  // Error::random(k)
     ctx->M.em_index = nullptr;
-    ctx->M.em_koff = nullptr;
+    ctx->M.em_kblob = nullptr;
     ctx->have_error = true;
     return RR_OK;
   }
@@ -485,56 +485,57 @@ RR_API int rr_set_error_model(rr_ctx* ctx, uint32_t k, uint64_t n_keys, const ui
       !upload(ctx, ctx->d_em_piece_begin, piece_begin) || !upload(ctx, ctx->d_em_piece_off, piece_off) ||
       !upload(ctx, ctx->d_em_piece_edits, piece_edits) || !upload(ctx, ctx->d_em_piece_ops, piece_ops))
     return fail(ctx, RR_ERR_CUDA, "rr_set_error_model: upload failed");
-  // packed records (DeviceModels::em_koff): same content, three dependent loads per event
-  ctx->M.em_koff = nullptr;
+  // packed records (DeviceModels::em_kblob): same content, two dependent loads per event
   ctx->M.em_kblob = nullptr;
   ctx->M.em_arec = nullptr;
+  ctx->M.em_kstride = 0;
   bool packable = k <= EM_PACK_K;
   for (uint32_t j = 0; j < n_alts && packable; ++j) packable = alt_off[j + 1] - alt_off[j] <= EM_PACK_ALT;
   if (packable) {
-    std::vector<uint32_t> koff(n_codes, EM_NO_KEY), arec((size_t)n_alts * EM_AREC_WORDS, 0);
-    std::vector<uint8_t> blob;
-    for (uint64_t code = 0; code < n_codes; ++code) {
-      const int32_t i = index[code];
-      if (i < 0) continue;
-      const uint32_t a0 = alt_begin[i], na = alt_begin[i + 1] - a0;
-      koff[code] = (uint32_t)(blob.size() / 16);
-      const size_t at = blob.size();
-      blob.resize(at + 16 + (((size_t)na * 8 + 15) & ~(size_t)15));
-      std::memcpy(&blob[at], &na, 4);
-      std::memcpy(&blob[at + 4], &a0, 4);
-      std::memcpy(&blob[at + 8], &scale[i], 8);
-      std::memcpy(&blob[at + 16], &cum[a0], (size_t)na * 8);
-    }
-    if (blob.size() / 16 >= EM_NO_KEY) return fail(ctx, RR_ERR_UNSUPPORTED, "rr_set_error_model: model too large for the packed tables");
-    blob.resize(blob.size() + 32 * 8 + 16, 0);  // 32 sums are read past any header
-    for (uint32_t j = 0; j < n_alts; ++j) {
-      uint32_t* r = &arec[(size_t)j * EM_AREC_WORDS];
-      uint8_t* rb = reinterpret_cast<uint8_t*>(r);
-      const uint32_t al = alt_off[j + 1] - alt_off[j];
-      std::memcpy(rb, alt_bytes + alt_off[j], al);
-      rb[15] = (uint8_t)al;
-      uint16_t* meta = reinterpret_cast<uint16_t*>(r + 12);
-      for (uint32_t es = 0; es < 8; ++es) {
-        const uint32_t pi = piece_begin[j] + es;
-        if (pi >= piece_begin[j + 1]) break;  // piece offsets that cannot occur for this alternative
-        const uint32_t o0 = piece_off[pi], no = piece_off[pi + 1] - o0;
-        if (no > 16) continue;  // entry stays invalid: the kernel aligns such a piece like any other merge
-        uint32_t ops = 0;
-        for (uint32_t x = 0; x < no; ++x) {
-          const uint8_t op = piece_ops[o0 + x];
-          ops |= (op == '=' ? 0u : op == 'X' ? 1u : op == 'I' ? 2u : 3u) << (2 * x);
-        }
-        r[4 + es] = ops;
-        meta[es] = (uint16_t)(no | ((uint32_t)piece_edits[pi] << 5) | 0x8000u);
+    uint32_t max_na = 0;
+    for (uint64_t i = 0; i < n_keys; ++i) max_na = std::max(max_na, alt_begin[i + 1] - alt_begin[i]);
+    const uint32_t stride = 16 + 8 * std::max(32u, (max_na + 1u) & ~1u);  // every lane may read one sum past the header
+    if ((uint64_t)stride * n_codes > (1ull << 31)) packable = false;      // a model with thousands of alternatives per k-mer: plain tables
+    if (packable) {
+      std::vector<uint32_t> arec((size_t)n_alts * EM_AREC_WORDS, 0);
+      std::vector<uint8_t> blob((size_t)stride * n_codes, 0);
+      for (uint64_t code = 0; code < n_codes; ++code) {
+        const int32_t i = index[code];
+        if (i < 0) continue;  // alternatives = 0: not in the model
+        const uint32_t a0 = alt_begin[i], na = alt_begin[i + 1] - a0;
+        uint8_t* at = &blob[(size_t)stride * code];
+        std::memcpy(at, &na, 4);
+        std::memcpy(at + 4, &a0, 4);
+        std::memcpy(at + 8, &scale[i], 8);
+        std::memcpy(at + 16, &cum[a0], (size_t)na * 8);
       }
-    }
-    if (!upload(ctx, ctx->d_em_koff, koff) || !upload(ctx, ctx->d_em_kblob, blob) || !upload(ctx, ctx->d_em_arec, arec))
-      return fail(ctx, RR_ERR_CUDA, "rr_set_error_model: upload failed");
-    if (!std::getenv("RR_NO_PACKED_MODEL")) {  // developer A/B: the unpacked tables
-      ctx->M.em_koff = ctx->d_em_koff.as<uint32_t>();
-      ctx->M.em_kblob = ctx->d_em_kblob.as<uint8_t>();
-      ctx->M.em_arec = ctx->d_em_arec.as<uint32_t>();
+      for (uint32_t j = 0; j < n_alts; ++j) {
+        uint32_t* r = &arec[(size_t)j * EM_AREC_WORDS];
+        uint8_t* rb = reinterpret_cast<uint8_t*>(r);
+        const uint32_t al = alt_off[j + 1] - alt_off[j];
+        std::memcpy(rb, alt_bytes + alt_off[j], al);
+        rb[15] = (uint8_t)al;
+        uint16_t* meta = reinterpret_cast<uint16_t*>(r + 12);
+        for (uint32_t es = 0; es < 8; ++es) {
+          const uint32_t pi = piece_begin[j] + es;
+          if (pi >= piece_begin[j + 1]) break;  // piece offsets that cannot occur for this alternative
+          const uint32_t o0 = piece_off[pi], no = piece_off[pi + 1] - o0;
+          if (no > 16) continue;  // entry stays invalid: the kernel aligns such a piece like any other merge
+          uint32_t ops = 0;
+          for (uint32_t x = 0; x < no; ++x) {
+            const uint8_t op = piece_ops[o0 + x];
+            ops |= (op == '=' ? 0u : op == 'X' ? 1u : op == 'I' ? 2u : 3u) << (2 * x);
+          }
+          r[4 + es] = ops;
+          meta[es] = (uint16_t)(no | ((uint32_t)piece_edits[pi] << 5) | 0x8000u);
+        }
+      }
+      if (!upload(ctx, ctx->d_em_kblob, blob) || !upload(ctx, ctx->d_em_arec, arec)) return fail(ctx, RR_ERR_CUDA, "rr_set_error_model: upload failed");
+      if (!std::getenv("RR_NO_PACKED_MODEL")) {  // developer A/B: the unpacked tables
+        ctx->M.em_kblob = ctx->d_em_kblob.as<uint8_t>();
+        ctx->M.em_kstride = stride;
+        ctx->M.em_arec = ctx->d_em_arec.as<uint32_t>();
+      }
     }
   }
   ctx->M.em_index = ctx->d_em_index.as<int32_t>();
@@ -869,7 +870,7 @@ static int enqueue(rr_ctx* ctx, Slot& sl) {
   CK(cudaEventRecord(sl.ev[0], sl.stream));
   const bool k7 = ctx->M.k == 7;
   auto* read_kernel = !ctx->M.em_index ? (k7 ? rr_read_kernel<EM_RANDOM, 7> : rr_read_kernel<EM_RANDOM, 0>)
-                      : ctx->M.em_koff ? (k7 ? rr_read_kernel<EM_PACKED, 7> : rr_read_kernel<EM_PACKED, 0>)
+                      : ctx->M.em_kblob ? (k7 ? rr_read_kernel<EM_PACKED, 7> : rr_read_kernel<EM_PACKED, 0>)
                                        : (k7 ? rr_read_kernel<EM_TABLES, 7> : rr_read_kernel<EM_TABLES, 0>);
   read_kernel<<<sl.read_grid, WARPS_PER_BLOCK * 32, READ_KERNEL_SMEM, sl.stream>>>(P);
   CK(cudaGetLastError());

@@ -724,7 +724,9 @@ __device__ __forceinline__ void process_read(const ReadKernelParams& P, WarpSmem
         uint32_t c = 0, olen, fk, fep;
         bool ok = true;
         int key = -1;
-        uint32_t koff = EM_NO_KEY;
+        uint2 hd = make_uint2(0u, 0u);  // packed tables: alternatives of the k-mer (0: not in the model), id of the first one
+        double scale = 0.0, cm = 0.0;
+        const double* cump = nullptr;
         if (EM != EM_RANDOM) {  // 2-bit code of the k-mer; any byte outside ACGT misses the table
           uint32_t part = 0, bad = 0;
           if ((uint32_t)lane < k) {
@@ -734,16 +736,16 @@ __device__ __forceinline__ void process_read(const ReadKernelParams& P, WarpSmem
           }
           const uint32_t code = __reduce_or_sync(0xffffffffu, part);
           if (!__any_sync(0xffffffffu, bad)) {
-            if (EM == EM_PACKED) koff = __ldg(M.em_koff + code);  // packed tables: key record
-            else key = M.em_index[code];
+            if (EM == EM_PACKED) {  // key record, directly indexed; its first 32 partial sums travel with the header
+              const uint8_t* kp = M.em_kblob + (size_t)code * M.em_kstride;
+              hd = __ldg(reinterpret_cast<const uint2*>(kp));
+              scale = __ldg(reinterpret_cast<const double*>(kp + 8));
+              cump = reinterpret_cast<const double*>(kp + 16);
+              cm = __ldg(cump + lane);
+            } else key = M.em_index[code];
           }
         }
-        if (EM == EM_PACKED && koff != EM_NO_KEY) {  // one WeightedIndex draw over the alternatives of the k-mer (src/model/error.rs:96-100)
-          const uint8_t* kp = M.em_kblob + (size_t)koff * 16u;
-          const uint2 hd = __ldg(reinterpret_cast<const uint2*>(kp));  // alternatives, id of the first one
-          const double scale = __ldg(reinterpret_cast<const double*>(kp + 8));
-          const double* cump = reinterpret_cast<const double*>(kp + 16);
-          double cm = __ldg(cump + lane);  // the first 32 partial sums travel with the header (the blob is padded)
+        if (EM == EM_PACKED && hd.x != 0) {  // one WeightedIndex draw over the alternatives of the k-mer (src/model/error.rs:96-100)
           const uint32_t na = hd.x;
           const uint64_t v2 = (uint64_t)ws->rng[W.off] | ((uint64_t)ws->rng[W.off + 1] << 32);  // first attempt: resident (HOT_FIRST)
           W.off += 2;
