@@ -291,6 +291,14 @@ def test_synthetic_badread_scale_models(orc):
     ctx.close()
 
 
+def _free_port():
+    import socket
+
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
 def _long_alt_model(k, seed=5):
     """Every k-mer in the table; alternatives of 0..64 bytes (longer than a warp: the memory path of add_change), several edits."""
     rnd = random.Random(seed)
@@ -687,7 +695,7 @@ def test_two_gpu_cli_matches_oracle(orc, rr, tmp_path, mode):
     ref = tmp_path / "ref.fasta"
     ref.write_text(fasta)
     out = tmp_path / "reads.fastq"
-    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1", "--master-port", "29541",
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1", "--master-port", str(_free_port()),
            "-m", "rustyread_b200", "simulate", "--reference", str(ref), "--quantity", "12x", "--seed", "21", "--error_model", "random",
            "--qscore_model", "random", "--output", str(out), "--number_base_store", "700K"]
     env = dict(os.environ)

@@ -14,6 +14,15 @@ import helpers
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
+
+def free_port():
+    """A TCP port nobody listens on right now (a fixed one can still be in TIME_WAIT from the previous run of the suite)."""
+    import socket
+
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
 WORKER = textwrap.dedent('''
     import io, os, sys
     sys.path.insert(0, %(root)r); sys.path.insert(0, os.path.join(%(root)r, "tests"))
@@ -154,7 +163,7 @@ SEEDLESS_WORKER = textwrap.dedent('''
     dist.init_process_group("gloo")
     if rank == 1:
         time.sleep(1.2)  # the ranks read the clock in different seconds
-    print("SEED", rank, S.agree_on_seed(dist, rank, world), flush=True)
+    open(os.path.join(%(out)r, "seed_%%d" %% rank), "w").write(str(S.agree_on_seed(dist, rank, world)))
     dist.destroy_process_group()
 ''')
 
@@ -162,15 +171,13 @@ SEEDLESS_WORKER = textwrap.dedent('''
 def test_ranks_agree_on_the_time_seed(tmp_path):
     """No --seed under torchrun: rank 0 reads the clock, everybody uses its value (src/simulate/mod.rs:31-36 has one process)."""
     wpath = tmp_path / "seedless.py"
-    wpath.write_text(SEEDLESS_WORKER % dict(root=ROOT))
+    wpath.write_text(SEEDLESS_WORKER % dict(root=ROOT, out=str(tmp_path)))
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
-           "--master-port", "29511", str(wpath)]
+           "--master-port", str(free_port()), str(wpath)]
     r = subprocess.run(cmd, env=dict(os.environ, MASTER_ADDR="127.0.0.1"), capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
-    import re
-
-    seeds = dict((int(a), int(b)) for a, b in re.findall(r"SEED (\d) (\d+)", r.stdout))
-    assert set(seeds) == {0, 1} and seeds[0] == seeds[1]
+    seeds = [int((tmp_path / ("seed_%d" % i)).read_text()) for i in range(2)]
+    assert seeds[0] == seeds[1] and abs(seeds[0] - __import__("time").time()) < 120
     from rustyread_b200.simulate import agree_on_seed
 
     assert abs(agree_on_seed(None, 0, 1) - __import__("time").time()) < 5
@@ -189,7 +196,7 @@ def test_world_size_2_simulate_matches_single_process(orc, tmp_path, parallel, w
     wpath.write_text(WORKER % dict(root=ROOT, fasta=str(fpath), out=str(opath), parallel=parallel, chunk=chunk))
     env = dict(os.environ, MASTER_ADDR="127.0.0.1")
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=%d" % world, "--master-addr", "127.0.0.1",
-           "--master-port", str(29517 + 2 * world + int(parallel)), str(wpath)]
+           "--master-port", str(free_port()), str(wpath)]
     r = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     params = dict(seed=9, length="2500,2200", quantity="10x", junk_reads=5, random_reads=5, chimera=10, glitches="900,25,25", threads=2,
