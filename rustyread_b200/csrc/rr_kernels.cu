@@ -76,7 +76,7 @@ struct rr_ctx {
   DevBuf d_em_kblob, d_em_arec;
   DevBuf d_adapter;
   DevBuf d_lcs_tab;
-  DevBuf d_q_tab_off, d_q_tab, d_q_dist_off, d_q_scores, d_q_cum, d_q_scale, d_q_unit, d_q_guide;
+  DevBuf d_q_tab_off, d_q_tab, d_q_dist_off, d_q_scores, d_q_cum, d_q_scale, d_q_unit, d_q_guide, d_q_tab32, d_q_rec;
 
   // Up to two batches in flight (rr_submit / rr_collect): all per-batch state, arenas and scratch included, lives in a
   // slot; the D2H of batch i (copy stream) overlaps the kernels of batch i+1 (the other slot's compute stream).
@@ -298,7 +298,7 @@ RR_API void rr_destroy(rr_ctx* ctx) {
   DevBuf* bufs[] = {&ctx->d_ref, &ctx->d_ref_off, &ctx->d_ref_circ, &ctx->d_em_index, &ctx->d_em_alt_begin, &ctx->d_em_alt_off,
                     &ctx->d_em_alt_bytes, &ctx->d_em_cum, &ctx->d_em_scale, &ctx->d_em_piece_begin, &ctx->d_em_piece_off, &ctx->d_em_piece_edits,
                     &ctx->d_em_piece_ops, &ctx->d_em_kblob, &ctx->d_em_arec, &ctx->d_adapter, &ctx->d_lcs_tab, &ctx->d_q_tab_off, &ctx->d_q_tab,
-                    &ctx->d_q_dist_off, &ctx->d_q_scores, &ctx->d_q_cum, &ctx->d_q_scale, &ctx->d_q_unit, &ctx->d_q_guide,
+                    &ctx->d_q_dist_off, &ctx->d_q_scores, &ctx->d_q_cum, &ctx->d_q_scale, &ctx->d_q_unit, &ctx->d_q_guide, &ctx->d_q_tab32, &ctx->d_q_rec,
                     &ctx->d_sc_rows, &ctx->d_sc_ops};
   for (auto* b : bufs) b->release();
   for (auto& sl : ctx->slot) {
@@ -626,6 +626,30 @@ RR_API int rr_set_qscore_model(rr_ctx* ctx, uint32_t max_k, uint64_t n, const ui
     }
     guide[i * (Q_GUIDE + 1) + Q_GUIDE] = (uint16_t)(nd - 1);
   }
+  // one record per distribution + the window table pointing straight at the records (QscoreModelDev::qrec)
+  std::vector<uint32_t> rec_off(n, Q_NO_REC), tab32(tab.size(), Q_NO_REC);
+  std::vector<uint8_t> qrec;
+  for (uint64_t i = 0; i < n; ++i) {
+    const uint32_t a0 = score_off[i], nd = score_off[i + 1] - score_off[i];
+    if (!dist_ok[i] || nd == 0) continue;
+    rec_off[i] = (uint32_t)(qrec.size() / 16);
+    const size_t at = qrec.size();
+    qrec.resize(at + 16 * (size_t)(Q_REC_HEAD + nd), 0);
+    std::memcpy(&qrec[at], &scale[i], 8);
+    std::memcpy(&qrec[at + 8], &qd[i].nd_unit, 4);
+    std::memcpy(&qrec[at + 16], &guide[i * (Q_GUIDE + 1)], (Q_GUIDE + 1) * 2);
+    for (uint32_t j = 0; j < nd; ++j) {
+      const uint64_t sc8 = scores[a0 + j];
+      std::memcpy(&qrec[at + 16 * (Q_REC_HEAD + j)], &cum[a0 + j], 8);
+      std::memcpy(&qrec[at + 16 * (Q_REC_HEAD + j) + 8], &sc8, 8);
+    }
+  }
+  if (qrec.size() / 16 >= Q_NO_REC) return fail(ctx, RR_ERR_UNSUPPORTED, "rr_set_qscore_model: model too large");
+  qrec.resize(qrec.size() + 64, 0);
+  for (size_t x = 0; x < tab.size(); ++x) if (tab[x] != 0xFFFF) tab32[x] = rec_off[tab[x]];
+  if (!upload(ctx, ctx->d_q_tab32, tab32) || !upload(ctx, ctx->d_q_rec, qrec)) return fail(ctx, RR_ERR_CUDA, "rr_set_qscore_model: upload failed");
+  ctx->Q.tab32 = ctx->d_q_tab32.as<uint32_t>();
+  ctx->Q.qrec = ctx->d_q_rec.as<uint8_t>();
   if (!upload(ctx, ctx->d_q_tab_off, tab_off) || !upload(ctx, ctx->d_q_tab, tab) || !upload(ctx, ctx->d_q_dist_off, qd) ||
       !upload(ctx, ctx->d_q_scores, sc) || !upload(ctx, ctx->d_q_cum, cum) || !upload(ctx, ctx->d_q_guide, guide))
     return fail(ctx, RR_ERR_CUDA, "rr_set_qscore_model: upload failed");

@@ -44,7 +44,13 @@ struct QscoreModelDev {
   // guide[Q_GUIDE] = count - 1.  A draw u in [g / Q_GUIDE, (g + 1) / Q_GUIDE) selects an index in [guide[g], guide[g + 1]]
   // (u * scale and the count are monotone), so the search over ~45 scores shrinks to the one or two that share a bucket.
   const uint16_t* guide;
+  // The same model as one record per distribution, for models that do not fit shared memory (a draw then costs three dependent
+  // L2 round trips instead of five): tab32 maps a window straight to its record (offset in 16-byte units, Q_NO_REC = unknown);
+  // record = {f64 scale, u32 count | unit flag, u32 0}, 17 u16 search bounds (48 bytes), then count pairs {f64 partial sum, u64 score}.
+  const uint32_t* tab32;
+  const uint8_t* qrec;
 };
+constexpr uint32_t Q_NO_REC = 0xffffffffu, Q_REC_HEAD = 4;  // 16-byte units before the pairs
 constexpr uint32_t Q_GUIDE = 16;
 
 struct QscoreKernelParams {
@@ -85,12 +91,12 @@ __global__ void __launch_bounds__(Q_THREADS, RR_Q_MINB) rr_qscore_kernel(const _
     for (uint32_t i = tid; i < Q.n_dist; i += Q_THREADS) s_dist[i] = Q.dist[i];
     for (uint32_t i = tid; i < Q.n_scores; i += Q_THREADS) s_scores[i] = Q.scores[i];
   }
-  uint32_t dsym0 = 0xFFFFu, dsym1 = 0xFFFFu, dsym2 = 0xFFFFu;  // K1: distribution of '=', 'X', 'I'
+  uint32_t dsym0 = 0xFFFFu, dsym1 = 0xFFFFu, dsym2 = 0xFFFFu;  // K1: distribution (CACHED) or record (!CACHED) of '=', 'X', 'I'
   if (K1) {
     const uint32_t o = Q.tab_off[1];
-    dsym0 = Q.tab[o];
-    dsym1 = Q.tab[o + 1];
-    dsym2 = Q.tab[o + 2];
+    dsym0 = CACHED ? (uint32_t)Q.tab[o] : Q.tab32[o];
+    dsym1 = CACHED ? (uint32_t)Q.tab[o + 1] : Q.tab32[o + 1];
+    dsym2 = CACHED ? (uint32_t)Q.tab[o + 2] : Q.tab32[o + 2];
   }
 
   for (;;) {
@@ -226,29 +232,48 @@ __global__ void __launch_bounds__(Q_THREADS, RR_Q_MINB) rr_qscore_kernel(const _
           const uint32_t len = 2 * half + 1;
           // ops p0 + x - half .. p0 + x + half = symbols 8 + x - half .. of the thread's 24-symbol word
           const uint32_t code = (uint32_t)(syms >> (2 * (8 + x - half))) & ((1u << (2 * len)) - 1u);
-          dist = Q.tab[Q.tab_off[len] + code];
+          dist = CACHED ? (uint32_t)Q.tab[Q.tab_off[len] + code] : __ldg(Q.tab32 + Q.tab_off[len] + code);
         }
         uint32_t qv = '!';
-        if (dist == 0xFFFFu) {
+        if (dist == (CACHED ? 0xFFFFu : Q_NO_REC)) {
           P.status[ridx] = ST_QUAL;
         } else {
           const uint64_t v = (uint64_t)s_words[woff] | ((uint64_t)s_words[woff + 1] << 32);
-          const QDist d = CACHED ? s_dist[dist] : Q.dist[dist];
-          const uint32_t hi = (d.nd_unit & 0x7fffffffu) - 1;
-          const double chosen = u64_to_unit12(v) * d.scale + 0.0;
-          uint32_t lo = 0;  // partition_point over the first nd - 1 partial sums
-          if (d.nd_unit >> 31) {
-            lo = min((uint32_t)chosen, hi);  // partial sums are exactly 1, 2, ..: #{i : i + 1 <= chosen} = floor(chosen)
-          } else {
-            const uint16_t* gd = Q.guide + (size_t)dist * (Q_GUIDE + 1u) + (uint32_t)(u64_to_unit12(v) * (double)Q_GUIDE);
-            lo = gd[0];
-            uint32_t up = gd[1];
-            while (lo < up) {
-              uint32_t mid = (lo + up) >> 1;
-              if (Q.cum[d.d0 + mid] <= chosen) lo = mid + 1; else up = mid;
+          if constexpr (CACHED) {
+            const QDist d = s_dist[dist];
+            const uint32_t hi = (d.nd_unit & 0x7fffffffu) - 1;
+            const double chosen = u64_to_unit12(v) * d.scale + 0.0;
+            uint32_t lo = 0;  // partition_point over the first nd - 1 partial sums
+            if (d.nd_unit >> 31) {
+              lo = min((uint32_t)chosen, hi);  // partial sums are exactly 1, 2, ..: #{i : i + 1 <= chosen} = floor(chosen)
+            } else {
+              const uint16_t* gd = Q.guide + (size_t)dist * (Q_GUIDE + 1u) + (uint32_t)(u64_to_unit12(v) * (double)Q_GUIDE);
+              lo = gd[0];
+              uint32_t up = gd[1];
+              while (lo < up) {
+                uint32_t mid = (lo + up) >> 1;
+                if (Q.cum[d.d0 + mid] <= chosen) lo = mid + 1; else up = mid;
+              }
             }
+            qv = s_scores[d.d0 + lo] + 33u;
+          } else {  // one record per distribution: header + search bounds, then {partial sum, score} pairs
+            const uint4* rec = reinterpret_cast<const uint4*>(Q.qrec) + dist;
+            const double u = u64_to_unit12(v);
+            const uint16_t* gd = reinterpret_cast<const uint16_t*>(rec + 1) + (uint32_t)(u * (double)Q_GUIDE);
+            const uint4 h = __ldg(rec);
+            uint32_t lo = __ldg(gd), up = __ldg(gd + 1);  // in flight together with the header
+            const uint32_t hi = (h.z & 0x7fffffffu) - 1;
+            const double chosen = u * __hiloint2double((int)h.y, (int)h.x) + 0.0;
+            if (h.z >> 31) {
+              lo = min((uint32_t)chosen, hi);
+            } else {
+              while (lo < up) {
+                const uint32_t mid = (lo + up) >> 1;
+                if (__ldg(reinterpret_cast<const double*>(rec + Q_REC_HEAD + mid)) <= chosen) lo = mid + 1; else up = mid;
+              }
+            }
+            qv = (__ldg(reinterpret_cast<const uint32_t*>(rec + Q_REC_HEAD + lo) + 2) & 0xffu) + 33u;
           }
-          qv = (CACHED ? s_scores[d.d0 + lo] : Q.scores[d.d0 + lo]) + 33u;
         }
         if (qi < elen) qual[qi] = (uint8_t)qv;
         woff += 2;
