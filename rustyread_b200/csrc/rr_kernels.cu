@@ -98,7 +98,7 @@ struct rr_ctx {
     DevBuf d_raw, d_err, d_cig;
     DevBuf d_sc_rows, d_sc_ops, d_sc_grec, d_sc_gseq;
     uint64_t sc_grec_alloc = 0, sc_gseq_alloc = 0;  // per-warp capacities the scratch is allocated for
-    // Heaviest read's work over a warp's share of the batch's work (plan()).  Above g_overlap_ratio the batch ends in a long
+    // Heaviest read's work over a warp's share of the batch's work (plan()).  Above g_overlap_ratio (2: the chain of the heaviest read is then about 1.5 x the balanced kernel time) the batch ends in a long
     // tail (a few warps walking the heaviest reads, the rest of the GPU idle), and the next batch's read kernel is allowed to
     // start behind it; otherwise the next batch waits, so that this batch's qscore kernel is not locked out by the next read
     // kernel's persistent blocks (measured on the bench workload: 18.2 -> 14.3 Gbases/s host to host when they overlap).
@@ -138,7 +138,7 @@ static const bool g_trace = std::getenv("RR_TRACE") != nullptr;
 static const uint32_t g_fast_warps = std::getenv("RR_FAST_WARPS") ? (uint32_t)std::atoi(std::getenv("RR_FAST_WARPS")) : (uint32_t)std::max(1, WARPS_PER_BLOCK / 2);
 static const double g_fast_threshold = std::getenv("RR_FAST_THRESHOLD") ? std::atof(std::getenv("RR_FAST_THRESHOLD")) : 0.7;
 static const bool g_no_fast_lanes = std::getenv("RR_NO_FAST_LANES") != nullptr;
-static const double g_overlap_ratio = std::getenv("RR_OVERLAP_RATIO") ? std::atof(std::getenv("RR_OVERLAP_RATIO")) : 1.5;  // developer aid: A/B of the read kernel's fast lanes
+static const double g_overlap_ratio = std::getenv("RR_OVERLAP_RATIO") ? std::atof(std::getenv("RR_OVERLAP_RATIO")) : 2.0;  // developer aid: A/B of the read kernel's fast lanes
 static void trace(const char* what, uint64_t batch) {
   if (!g_trace) return;
   timespec ts;
@@ -782,6 +782,8 @@ static int plan(rr_ctx* ctx, Slot& sl) {
     for (uint64_t i = 0; i < n; ++i) total += work[i];
     const double share = total / n_warps;
     sl.tail_ratio = (n && share > 0) ? work[sl.h_order[0]] / share : 0.0;  // heaviest read against a warp's share of the batch
+    if (g_trace) std::fprintf(stderr, "[rr] plan: %llu reads, heaviest read / warp share = %.2f (next batch may overlap above %.2f)\n",
+                              (unsigned long long)n, sl.tail_ratio, g_overlap_ratio);
     uint64_t nh = 0;
     double heavy = 0;
     while (nh < n && work[sl.h_order[nh]] > g_fast_threshold * share) heavy += work[sl.h_order[nh++]];
