@@ -574,7 +574,7 @@ __device__ __forceinline__ uint32_t add_change_reg(Walk& W, WarpSmem* ws, const 
         }
         nops = fk == 2 ? add : tn;  // substitution / deletion: one op per raw base, insertion: one per piece base
         ed = has_edit ? 1u : 0u;
-        if (emit && has_edit) ws->cigb[(S.cig_len + at) & (RING - 1u)] = fk == 1 ? 'X' : fk == 2 ? 'I' : 'D';
+        if (emit && has_edit) ws->cigb[(S.cig_len + at) & (RING - 1u)] = (uint8_t)(0x44495800u >> (8u * fk));  // fk 1 'X', 2 'I', 3 'D'
       } else if ((add == 0 || tn == 0) && add + tn <= 32u) {  // all deletions / all insertions
         nops = add + tn;
         ed = nops;
