@@ -137,8 +137,8 @@ struct rr_ctx {
 static const bool g_trace = std::getenv("RR_TRACE") != nullptr;
 static const uint32_t g_fast_warps = std::getenv("RR_FAST_WARPS") ? (uint32_t)std::atoi(std::getenv("RR_FAST_WARPS")) : (uint32_t)std::max(1, WARPS_PER_BLOCK / 2);
 static const double g_fast_threshold = std::getenv("RR_FAST_THRESHOLD") ? std::atof(std::getenv("RR_FAST_THRESHOLD")) : 0.7;
-static const bool g_no_fast_lanes = std::getenv("RR_NO_FAST_LANES") != nullptr;
-static const double g_overlap_ratio = std::getenv("RR_OVERLAP_RATIO") ? std::atof(std::getenv("RR_OVERLAP_RATIO")) : 2.0;  // developer aid: A/B of the read kernel's fast lanes
+static const bool g_no_fast_lanes = std::getenv("RR_NO_FAST_LANES") != nullptr;  // developer aid: A/B of the read kernel's fast lanes
+static const double g_overlap_ratio = std::getenv("RR_OVERLAP_RATIO") ? std::atof(std::getenv("RR_OVERLAP_RATIO")) : 2.0;  // see Slot::tail_ratio
 static void trace(const char* what, uint64_t batch) {
   if (!g_trace) return;
   timespec ts;

@@ -11,7 +11,8 @@ for out in ("/dev/null", "/dev/shm/rr_reads.fastq"):
                         "--qscore_model", "random", "--output", out], capture_output=True, text=True, env=dict(os.environ, RUSTYREAD_B200_TIMING="1"), cwd=os.path.join(os.path.dirname(__file__), ".."))
     dt = time.time() - t
     print(out, "rc", r.returncode, r.stderr.strip()[-400:], "wall %.2fs" % dt)
-    bases = int(r.stderr.strip().split()[-2]) if r.returncode == 0 else 0
+    wrote = [l for l in r.stderr.splitlines() if l.startswith("wrote")]
+    bases = int(wrote[-1].split()[-2]) if (r.returncode == 0 and wrote) else 0
     print("  -> %.2f Gbases/s whole process (incl. python start, reference parse, 100k length draws, context creation)" % (bases / dt / 1e9))
     if out != "/dev/null" and os.path.exists(out):
         print("  file size %.2f GB" % (os.path.getsize(out) / 1e9)); os.remove(out)
