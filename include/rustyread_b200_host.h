@@ -82,6 +82,12 @@ int rr_sim_fastq(rr_sim* s, const rr_batch* batch, uint64_t first, const char** 
  * buffer, sequence and quality bytes are sent from the batch's (pinned) arenas without an intermediate copy. */
 int rr_sim_write_fastq(rr_sim* s, const rr_batch* batch, uint64_t first, int fd, uint64_t* n_records, uint64_t* n_bases,
                        uint64_t* n_bytes);
+/* threads > 1: on a regular file opened read-write (not for append) rr_sim_write_fastq grows the file to the end of the part,
+ * maps the part's byte range and copies contiguous ranges of records into the mapping from `threads` threads, then leaves the
+ * file position after the part (one writev stream fills the page cache at 2-4 GB/s and several streams into one file do no
+ * better; the parallel copy does).  Only for a file no other process resizes meanwhile.  Default 1: one writev stream, which is
+ * also what pipes, append-mode descriptors and small parts always get.  The bytes written are the same either way. */
+int rr_sim_set_writer_threads(rr_sim* s, int threads);
 
 /* Bytes, records and bases of the text rr_sim_fastq / rr_sim_write_fastq produce for items [first, first + n) of the last
  * feed, given their final lengths and identities; formats the comments only and draws nothing from main_rng (a read

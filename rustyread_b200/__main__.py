@@ -49,7 +49,7 @@ def main(argv=None):
     fasta = sim_mod.read_maybe_compressed(a.reference) if (rank == 0 or not share) else None  # niffler: plain, gz, bz2 or xz by magic number
     if os.environ.get("RUSTYREAD_B200_TIMING"):
         print("rustyread_b200 timing rank %d: reference read at %.3f s" % (rank, time.perf_counter() - t_start), file=sys.stderr, flush=True)
-    out = (open(a.output, "wb") if a.output else sys.stdout.buffer) if rank == 0 else None
+    out = (open(a.output, "w+b") if a.output else sys.stdout.buffer) if rank == 0 else None  # read-write: the threaded writer maps the file
     flags = {k: getattr(a, k) for k in d}
     chunk = int(os.environ.get("RUSTYREAD_B200_CHUNK_BASES", "1000000000"))  # device chunk size inside one reference batch
     # several ranks + a regular output file: every rank writes its own records in place (RUSTYREAD_B200_SINGLE_WRITER=1: gather on rank 0)

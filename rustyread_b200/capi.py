@@ -388,6 +388,7 @@ HOST_EXPORTS = {
     "rr_sim_fastq": (C.c_int, [C.c_void_p, C.POINTER(rr_batch), C.c_uint64, C.POINTER(C.c_void_p), u64p, u64p, u64p]),
     "rr_sim_write_fastq": (C.c_int, [C.c_void_p, C.POINTER(rr_batch), C.c_uint64, C.c_int, u64p, u64p, u64p]),
     "rr_sim_skip_names": (C.c_int, [C.c_void_p, C.c_uint64]),
+    "rr_sim_set_writer_threads": (C.c_int, [C.c_void_p, C.c_int]),
     "rr_sim_fastq_bytes": (C.c_int, [C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint64, u64p, u64p, u64p]),
     "rr_sim_item_description": (C.c_int, [C.c_void_p, C.c_uint64, C.c_char_p, C.c_uint64]),
     "rr_sim_n_refs": (C.c_uint64, [C.c_void_p]),
@@ -502,6 +503,10 @@ class Simulation:
         recs, bases, nbytes = C.c_uint64(), C.c_uint64(), C.c_uint64()
         self._ck(self.lib.dll.rr_sim_write_fastq(self.h, C.byref(batch_struct), first, fd, C.byref(recs), C.byref(bases), C.byref(nbytes)))
         return recs.value, bases.value, nbytes.value
+
+    def set_writer_threads(self, threads):
+        """Threads write_fastq may use on a regular file (contiguous record ranges sent to their offsets with pwritev)."""
+        self._ck(self.lib.dll.rr_sim_set_writer_threads(self.h, int(threads)))
 
     def fastq_bytes(self, lengths, real_identity, first=0):
         """(bytes, records, bases) of the FASTQ text for items [first, first + n) with these final lengths / identities."""

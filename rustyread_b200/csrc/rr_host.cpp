@@ -18,7 +18,11 @@
 #include <vector>
 
 #include <cerrno>
+#include <fcntl.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
 #include <sys/uio.h>
+#include <thread>
 #include <unistd.h>
 
 #include "../../include/rustyread_b200_host.h"
@@ -316,6 +320,8 @@ struct rr_sim {
   // last batch
   std::vector<rr_desc> items;
   std::string fastq;
+  // threads rr_sim_write_fastq may use on a regular file (rr_sim_set_writer_threads; 1 = one writev stream)
+  int writer_threads = 1;
 };
 
 static std::string g_sim_error;
@@ -779,74 +785,135 @@ RR_API int rr_sim_item_description(rr_sim* s, uint64_t i, char* out, uint64_t ca
   return RR_OK;
 }
 
+// Writes iov[0, n) to fd: at the file position (at < 0, writev) or at offset `at` (pwritev).  Short writes are continued.
+static const char* write_all(int fd, iovec* iov, size_t n, off_t at, uint64_t& bytes) {
+  size_t i = 0;
+  while (i < n) {
+    const int cnt = (int)std::min<size_t>(n - i, 1000);  // IOV_MAX is 1024
+    ssize_t w = at < 0 ? ::writev(fd, iov + i, cnt) : ::pwritev(fd, iov + i, cnt, at);
+    if (w < 0) {
+      if (errno == EINTR) continue;
+      return std::strerror(errno);
+    }
+    bytes += (uint64_t)w;
+    if (at >= 0) at += w;
+    size_t left = (size_t)w;
+    while (left > 0 && i < n) {
+      if (left >= iov[i].iov_len) { left -= iov[i].iov_len; ++i; }
+      else { iov[i].iov_base = (char*)iov[i].iov_base + left; iov[i].iov_len -= left; left = 0; }
+    }
+    while (i < n && iov[i].iov_len == 0) ++i;
+  }
+  return nullptr;
+}
+
+RR_API int rr_sim_set_writer_threads(rr_sim* s, int threads) {
+  if (!s || threads < 1) return RR_ERR_ARG;
+  s->writer_threads = threads;
+  return RR_OK;
+}
+
 RR_API int rr_sim_write_fastq(rr_sim* s, const rr_batch* b, uint64_t first, int fd, uint64_t* n_records, uint64_t* n_bases, uint64_t* n_bytes) {
   if (!s || !b) return RR_ERR_ARG;
   if (first + b->n_reads > s->items.size()) return sfail(s, RR_ERR_ARG, "rr_sim_write_fastq: batch does not match the last feed");
   const uint32_t k = b->k;
-  // headers for a block of records are laid out in one string; iovecs point into it and into the batch arenas
-  constexpr size_t BLOCK = 200;  // records per writev (5 iovecs each, IOV_MAX is 1024)
+  // Pass 1 (serial: read names come from main_rng in write order, mod.rs:199-203): the two header lines of every emitted record
+  // in one string, and the record's five pieces as iovecs that point into it and into the batch arenas (no copy of the payload).
   std::string& hdr = s->fastq;
-  std::vector<iovec> iov;
-  std::vector<size_t> hoff;  // per record: offset of "@uuid comment\n" and of "\n+ comment\n" in hdr
-  uint64_t recs = 0, bases = 0, bytes = 0;
+  hdr.clear();
+  std::vector<size_t> hoff;     // per record: offset of "@uuid comment\n", of "\n+ comment\n", and the end
+  std::vector<uint64_t> idx;    // emitted records
+  uint64_t bases = 0;
   static const char NL = '\n';
   std::string comment;
-  uint64_t i = 0;
-  while (i < b->n_reads) {
-    hdr.clear();
-    hoff.clear();
-    std::vector<uint64_t> idx;
-    for (; i < b->n_reads && idx.size() < BLOCK; ++i) {
-      const uint64_t l = b->lengths[i];
-      if (l <= 14) continue;  // mod.rs:192-194
-      if (l < 2ULL * k) return sfail(s, RR_ERR_READ, "rr_sim_write_fastq: read shorter than 2k (the reference panics slicing it)");
-      uint64_t lo = s->rng.next_u64(), hi = s->rng.next_u64();
-      uint8_t name[16];
-      for (int x = 0; x < 8; ++x) { name[x] = (uint8_t)(hi >> (56 - 8 * x)); name[8 + x] = (uint8_t)(lo >> (56 - 8 * x)); }
-      comment.clear();
-      append_description(s, comment, s->items[first + i], l, b->real_identity[i]);
-      hoff.push_back(hdr.size());
-      hdr += '@';
-      uuid_v3_x500(name, hdr);
-      hdr += ' ';
-      hdr += comment;
-      hdr += '\n';
-      hoff.push_back(hdr.size());
-      hdr += "\n+ ";
-      hdr += comment;
-      hdr += '\n';
-      hoff.push_back(hdr.size());
-      idx.push_back(i);
-    }
-    iov.clear();
-    for (size_t r = 0; r < idx.size(); ++r) {
-      const uint64_t j = idx[r], n = b->lengths[j] - 2ULL * k;
-      const char* h = hdr.data();
-      iov.push_back({(void*)(h + hoff[3 * r]), hoff[3 * r + 1] - hoff[3 * r]});
-      iov.push_back({(void*)(b->seq + b->offsets[j] + k), (size_t)n});
-      iov.push_back({(void*)(h + hoff[3 * r + 1]), hoff[3 * r + 2] - hoff[3 * r + 1]});
-      iov.push_back({(void*)(b->qual + b->offsets[j] + k), (size_t)n});
-      iov.push_back({(void*)&NL, 1});
-      ++recs;
-      bases += n;
-    }
-    size_t at = 0;
-    while (at < iov.size()) {  // writev may write less than asked
-      ssize_t w = ::writev(fd, iov.data() + at, (int)std::min<size_t>(iov.size() - at, 1000));
-      if (w < 0) {
-        if (errno == EINTR) continue;
-        return sfail(s, RR_ERR_ARG, std::string("rr_sim_write_fastq: writev failed: ") + std::strerror(errno));
-      }
-      bytes += (uint64_t)w;
-      size_t left = (size_t)w;
-      while (left > 0 && at < iov.size()) {
-        if (left >= iov[at].iov_len) { left -= iov[at].iov_len; ++at; }
-        else { iov[at].iov_base = (char*)iov[at].iov_base + left; iov[at].iov_len -= left; left = 0; }
-      }
-      while (at < iov.size() && iov[at].iov_len == 0) ++at;
+  for (uint64_t i = 0; i < b->n_reads; ++i) {
+    const uint64_t l = b->lengths[i];
+    if (l <= 14) continue;  // mod.rs:192-194
+    if (l < 2ULL * k) return sfail(s, RR_ERR_READ, "rr_sim_write_fastq: read shorter than 2k (the reference panics slicing it)");
+    uint64_t lo = s->rng.next_u64(), hi = s->rng.next_u64();
+    uint8_t name[16];
+    for (int x = 0; x < 8; ++x) { name[x] = (uint8_t)(hi >> (56 - 8 * x)); name[8 + x] = (uint8_t)(lo >> (56 - 8 * x)); }
+    comment.clear();
+    append_description(s, comment, s->items[first + i], l, b->real_identity[i]);
+    hoff.push_back(hdr.size());
+    hdr += '@';
+    uuid_v3_x500(name, hdr);
+    hdr += ' ';
+    hdr += comment;
+    hdr += '\n';
+    hoff.push_back(hdr.size());
+    hdr += "\n+ ";
+    hdr += comment;
+    hdr += '\n';
+    hoff.push_back(hdr.size());
+    idx.push_back(i);
+    bases += l - 2ULL * k;
+  }
+  const size_t nrec = idx.size();
+  std::vector<iovec> iov(5 * nrec);
+  std::vector<uint64_t> start(nrec + 1, 0);  // byte offset of every record inside this part
+  for (size_t r = 0; r < nrec; ++r) {
+    const uint64_t j = idx[r], n = b->lengths[j] - 2ULL * k;
+    const char* h = hdr.data();
+    iov[5 * r + 0] = {(void*)(h + hoff[3 * r]), hoff[3 * r + 1] - hoff[3 * r]};
+    iov[5 * r + 1] = {(void*)(b->seq + b->offsets[j] + k), (size_t)n};
+    iov[5 * r + 2] = {(void*)(h + hoff[3 * r + 1]), hoff[3 * r + 2] - hoff[3 * r + 1]};
+    iov[5 * r + 3] = {(void*)(b->qual + b->offsets[j] + k), (size_t)n};
+    iov[5 * r + 4] = {(void*)&NL, 1};
+    start[r + 1] = start[r] + (hoff[3 * r + 2] - hoff[3 * r]) + 2 * n + 1;
+  }
+  // Pass 2.  One writev stream fills the page cache at 2-4 GB/s, and several pwritev streams into ONE file do no better (buffered
+  // writes serialise on the inode lock).  What does scale is the copy itself: with rr_sim_set_writer_threads(> 1) a regular
+  // file is grown to the end of this part, the part's byte range is mapped, and the threads copy contiguous ranges of records
+  // into the mapping (page faults and copies of different ranges proceed in parallel).  Pipes, append-mode descriptors and
+  // small parts go through writev at the file position.  Requires that no other process resizes the file meanwhile.
+  uint64_t bytes = 0;
+  const uint64_t total = start[nrec];
+  int threads = s->writer_threads;
+  off_t base = -1;
+  if (threads > 1 && total >= (4u << 20)) {
+    struct stat st;
+    const int fl = ::fcntl(fd, F_GETFL);
+    if (::fstat(fd, &st) == 0 && S_ISREG(st.st_mode) && fl >= 0 && !(fl & O_APPEND) && (fl & O_ACCMODE) == O_RDWR) {
+      base = ::lseek(fd, 0, SEEK_CUR);
+      if (base >= 0 && st.st_size < base + (off_t)total && ::ftruncate(fd, base + (off_t)total) != 0) base = -1;
     }
   }
-  if (n_records) *n_records = recs;
+  char* map = nullptr;
+  size_t map_len = 0, map_skew = 0;
+  if (base >= 0) {
+    const long page = ::sysconf(_SC_PAGESIZE);
+    map_skew = (size_t)(base % page);
+    map_len = map_skew + total;
+    void* m = ::mmap(nullptr, map_len, PROT_READ | PROT_WRITE, MAP_SHARED, fd, base - (off_t)map_skew);
+    if (m == MAP_FAILED) base = -1; else map = (char*)m;
+  }
+  if (base < 0) {
+    if (const char* m = write_all(fd, iov.data(), iov.size(), -1, bytes)) return sfail(s, RR_ERR_ARG, std::string("rr_sim_write_fastq: writev failed: ") + m);
+  } else {
+    threads = (int)std::min<uint64_t>((uint64_t)threads, std::max<uint64_t>(1, total >> 20));
+    std::vector<size_t> cut(threads + 1, nrec);
+    cut[0] = 0;
+    for (int t = 1; t < threads; ++t)
+      cut[t] = (size_t)(std::lower_bound(start.begin(), start.end(), total * (uint64_t)t / (uint64_t)threads) - start.begin());
+    for (int t = 1; t <= threads; ++t) cut[t] = std::max(cut[t], cut[t - 1]);
+    std::vector<std::thread> pool;
+    auto work = [&](int t) {
+      char* dst = map + map_skew + start[cut[t]];
+      for (size_t x = 5 * cut[t]; x < 5 * cut[t + 1]; ++x) {
+        std::memcpy(dst, iov[x].iov_base, iov[x].iov_len);
+        dst += iov[x].iov_len;
+      }
+    };
+    for (int t = 1; t < threads; ++t) pool.emplace_back(work, t);
+    work(0);
+    for (auto& th : pool) th.join();
+    ::munmap(map, map_len);
+    bytes = total;
+    if (::lseek(fd, base + (off_t)total, SEEK_SET) < 0) return sfail(s, RR_ERR_ARG, std::string("rr_sim_write_fastq: lseek failed: ") + std::strerror(errno));
+  }
+  if (bytes != total) return sfail(s, RR_ERR_ARG, "rr_sim_write_fastq: short write");
+  if (n_records) *n_records = nrec;
   if (n_bases) *n_bases = bases;
   if (n_bytes) *n_bytes = bytes;
   return RR_OK;

@@ -311,6 +311,10 @@ def _simulate_single_gpu(sim, total, limit, output, device, chunk_bases):
         output.flush()
     except Exception:
         fd = None
+    if fd is not None:
+        # a regular output file is filled by several threads (rr_sim_set_writer_threads); this process is its only writer
+        wt = os.environ.get("RUSTYREAD_B200_WRITER_THREADS")
+        sim.set_writer_threads(int(wt) if wt else max(1, min(8, (os.cpu_count() or 2) // 2)))
     produced, n_reads, n_bases = 0, 0, 0
     while produced < total:
         base_loop = min(limit, total - produced)

@@ -596,8 +596,10 @@ def test_collect_meta_sizes_records_before_the_first_part(orc, tmp_path):
     ctx.close()
 
 
-def test_cli_simulate_matches_oracle(orc, tmp_path):
-    """`python -m rustyread_b200 simulate` (the drop-in CLI) writes the same file as the oracle's simulate()."""
+@pytest.mark.parametrize("quantity,store", [("15x", "500K"), ("90x", None)])
+def test_cli_simulate_matches_oracle(orc, tmp_path, quantity, store):
+    """`python -m rustyread_b200 simulate` (the drop-in CLI) writes the same file as the oracle's simulate(); the second case is
+    large enough (17 MB of FASTQ in one part) for the threaded writer, which maps the output file and copies into it."""
     import subprocess
     import sys
 
@@ -605,11 +607,15 @@ def test_cli_simulate_matches_oracle(orc, tmp_path):
     ref = tmp_path / "ref.fasta"
     ref.write_text(fasta)
     out = tmp_path / "reads.fastq"
-    cmd = [sys.executable, "-m", "rustyread_b200", "simulate", "--reference", str(ref), "--quantity", "15x", "--seed", "42", "--error_model", "random",
-           "--qscore_model", "random", "--output", str(out), "--number_base_store", "500K", "--chimera", "5"]
-    r = subprocess.run(cmd, capture_output=True, text=True, cwd=helpers.ROOT if hasattr(helpers, "ROOT") else None, timeout=600)
+    cmd = [sys.executable, "-m", "rustyread_b200", "simulate", "--reference", str(ref), "--quantity", quantity, "--seed", "42", "--error_model", "random",
+           "--qscore_model", "random", "--output", str(out), "--chimera", "5"] + (["--number_base_store", store] if store else [])
+    env = dict(__import__("os").environ, RUSTYREAD_B200_WRITER_THREADS="4")
+    r = subprocess.run(cmd, capture_output=True, text=True, cwd=helpers.ROOT if hasattr(helpers, "ROOT") else None, timeout=600, env=env)
     assert r.returncode == 0, r.stderr[-2000:]
-    text, stats = orc.simulate(dict(seed=42, quantity="15x", chimera=5, number_base_store="500K", threads=8), fasta, capture=True)
+    params = dict(seed=42, quantity=quantity, chimera=5, threads=8)
+    if store:
+        params["number_base_store"] = store
+    text, stats = orc.simulate(params, fasta, capture=True)
     assert out.read_text() == text and stats["reads"] > 50
 
 

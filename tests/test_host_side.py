@@ -276,3 +276,59 @@ def test_session_from_contig_index_is_the_same_session(orc, rr):
         assert a.rng_words() == b.rng_words()
     with pytest.raises(capi.RRError):
         capi.Simulation(None, index=[], **kw)
+
+
+def test_threaded_file_writer_writes_the_same_bytes(orc, rr, tmp_path):
+    """rr_sim_write_fastq: several threads sending record ranges to their offsets (regular file), one writev stream (pipe,
+    append mode, one thread) and rr_sim_fastq's text are the same bytes; the file position ends after the part."""
+    import rustyread_b200.capi as capi
+
+    fasta = helpers.random_fasta(orc, [60_000])
+    kw = dict(seed=5, length=(9000, 7000))
+    rs = np.random.RandomState(8)
+
+    def session():
+        s = capi.Simulation(fasta, **kw)
+        d = s.feed(12_000_000)
+        return s, d
+
+    s0, d = session()
+    lens = rs.randint(0, 20_000, size=len(d)).astype(np.uint64)
+    lens[::17] = rs.randint(0, 15, size=len(lens[::17]))  # reads of 14 bases or fewer are dropped (mod.rs:192-194)
+    lens[(lens > 14) & (lens < 2 * s0.k)] = 2 * s0.k
+    off = np.concatenate([[0], np.cumsum((lens + 15) // 16 * 16)]).astype(np.uint64)
+    seq = rs.choice(np.frombuffer(b"ACGT", np.uint8), size=int(off[-1]))
+    qual = rs.randint(34, 70, size=int(off[-1])).astype(np.uint8)
+    ident = rs.uniform(80, 99, size=len(d))
+    batch = lambda s: capi.batch_struct_from_arrays(off, lens, seq, qual, ident, s.k)
+    text, recs, bases = s0.fastq(batch(s0))
+    assert len(text) > (8 << 20) and recs > 500  # large enough for the threaded path
+    for mode in ("threads", "one-thread", "append", "pipe", "offset"):
+        s, _ = session()
+        s.set_writer_threads(1 if mode == "one-thread" else 5)
+        path = tmp_path / ("out_" + mode)
+        if mode == "pipe":
+            import threading
+
+            r, w = os.pipe()
+            got = []
+            t = threading.Thread(target=lambda: got.append(os.fdopen(r, "rb").read()))
+            t.start()
+            res = s.write_fastq(batch(s), w)
+            os.close(w)
+            t.join()
+            data = got[0]
+        else:
+            pre = b"HEADER\n" if mode == "offset" else b""
+            fd = os.open(str(path), os.O_RDWR | os.O_CREAT | (os.O_APPEND if mode == "append" else 0), 0o644)
+            os.write(fd, pre)
+            res = s.write_fastq(batch(s), fd)
+            assert os.lseek(fd, 0, os.SEEK_CUR) == len(pre) + len(text)
+            os.write(fd, b"TAIL")
+            os.close(fd)
+            data = path.read_bytes()
+            assert data.startswith(pre) and data.endswith(b"TAIL")
+            data = data[len(pre):-4]
+        assert res == (recs, bases, len(text)), mode
+        assert data == text, mode
+        assert s.rng_words() == s0.rng_words()
