@@ -959,6 +959,7 @@ static int finish(rr_ctx* ctx, Slot& sl) {
       const char* what = st[i] == ST_ALIGN_TOO_LARGE ? "alignment window beyond the bit-vector scratch (2048 columns)"
                          : st[i] == ST_REF_PANIC     ? "slice out of range in Change::merge/update_align (the reference panics here)"
                          : st[i] == ST_RNG_EXHAUSTED ? "an error event rejected more than 400 stream words in a row (internal limit; probability < 2^-130)"
+                         : st[i] == ST_QUAL_WINDOW   ? "CIGAR window slice out of range in generate_quality (src/simulate/quality.rs:22-34: the reference panics here)"
                                                      : "qscore window not in the model (reference: QualityNotMinimalCigarString)";
       std::snprintf(buf, sizeof buf, "read %llu (seed %llu): %s", (unsigned long long)i, (unsigned long long)sl.descs[i].seed, what);
       sl.enqueued = false;

@@ -225,7 +225,7 @@ __global__ void __launch_bounds__(Q_THREADS, RR_Q_MINB) rr_qscore_kernel(const _
             if (i < margin) half = i;
             else if (i >= n - margin) half = n - i - 1;  // wraps like the reference's usize when n < margin
             if (i < half || i + half + 1 > n) {          // the slice cigar[start..end] is out of range: the reference panics
-              P.status[ridx] = ST_REF_PANIC;
+              P.status[ridx] = ST_QUAL_WINDOW;
               half = 0;
             }
           }

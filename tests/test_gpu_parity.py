@@ -375,6 +375,37 @@ def test_packed_error_model_edges(orc, k):
     ctx.close()
 
 
+def test_qscore_window_panic_is_reported_for_the_same_read(orc):
+    """Reads of a handful of bases with a k = 3 model and 9-wide qscore windows: `generate_quality` slices its CIGAR out of range
+    (src/simulate/quality.rs:22-34, usize arithmetic) and the reference panics.  The device reports exactly the first read the
+    oracle fails on, names the place, and everything before that read is generated normally."""
+    import re
+
+    import rustyread_b200 as rr
+    import rustyread_b200.capi as capi
+
+    fasta = helpers.random_fasta(orc, [30_000])
+    adapter = ("AATGTACTTCGTTCAGTTACGTATTGCT", "GCAATACGTAACTGAACGAAGT", 10.0, 60.0, 10.0, 20.0)
+    spec = dict(seed=1, length=(12.0, 10.0), error_model=_long_alt_model(3, seed=1), qscore_model="ideal", identity=(70.0, 88.0, 9.0), adapter=adapter)
+    w, ctx, s = helpers.make_pair(orc, fasta, spec)
+    n = w.feed(3000)
+    d, ident, _ = w.items()
+    descs = capi.descs_from_oracle_items(d, ident)
+    with pytest.raises(rr.RRError) as e:
+        ctx.generate(descs)
+    assert "generate_quality" in str(e.value)
+    r = int(re.search(r"read (\d+) ", str(e.value)).group(1))
+    w.load_items(d[r:r + 1], ident[r:r + 1])
+    with pytest.raises(RuntimeError) as oe:
+        w.generate(threads=1)
+    assert "generate_quality" in str(oe.value)
+    assert r > 0
+    w.load_items(d[:r], ident[:r])
+    w.generate(threads=4)  # no error before read r
+    helpers.compare_batch(w, ctx.generate(descs[:r]), ctx)
+    ctx.close()
+
+
 def test_reference_with_bytes_outside_acgt(orc):
     # N runs, IUPAC codes and lower case pass through untouched (src/references.rs:162-166); k-mers that contain them miss the
     # error-model table and alignments that meet them leave the register aligner for the general one
