@@ -26,7 +26,7 @@ for seed in range(first, first + n_cases):
                 r = rnd.random()
                 lines[i] = "N" * len(lines[i]) if r < 0.3 else lines[i].lower() if r < 0.6 else "".join(rnd.choice("ACGTRYKMSWN") for _ in lines[i])
         fasta = "\n".join(lines)
-    mean = rnd.choice([800.0, 2500.0, 6000.0])
+    mean = rnd.choice([20000.0, 50000.0] if os.environ.get("FUZZ_LONG") else [800.0, 2500.0, 6000.0])  # FUZZ_LONG=1: ultra-long reads
     spec = dict(seed=seed, length=(mean, mean * rnd.choice([0.5, 0.9, 1.3])), identity=rnd.choice([(85.0, 95.0, 5.0), (70.0, 88.0, 9.0), (97.0, 100.0, 2.0), (99.0, 100.0, 0.5)]),
                 glitch=rnd.choice([(10000.0, 25.0, 25.0), (300.0, 40.0, 10.0), (0.0, 25.0, 25.0), (150.0, 5.0, 60.0)]),
                 rates=rnd.choice([(1.0, 1.0, 1.0), (10.0, 10.0, 20.0), (0.0, 0.0, 50.0)]), small_plasmid_bias=rnd.random() < 0.5)
@@ -38,7 +38,7 @@ for seed in range(first, first + n_cases):
     spec["qscore_model"] = rnd.choice(["random", "ideal", qscore_text])
     t = time.time()
     try:
-        target = rnd.choice([150_000, 400_000])
+        target = rnd.choice([2_000_000, 5_000_000] if os.environ.get("FUZZ_LONG") else [150_000, 400_000])
         w, ctx, batch, n = T._run_pair(orc, fasta, spec, target)
         ctx.close()
         print("case %3d ok: %d reads, %d bases, contigs %s circ %s error %s qscore %s identity %s glitch %s (%.1f s)" % (
