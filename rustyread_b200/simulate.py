@@ -405,7 +405,7 @@ def simulate(fasta, quantity, output, generate_factory=None, dist=None, rank=0, 
                 sim = capi.Simulation(fasta, **kw)
                 box = [sim.contig_index()]
             except Exception as e:  # the other ranks must not wait for an index that never comes
-                box = [e]
+                box = [RuntimeError("rank 0 could not load the reference: %s" % e)]  # a plain exception: it has to survive pickling
         lap("parse reference + models (rank 0)")
         dist.broadcast_object_list(box, 0)
         if isinstance(box[0], Exception):
