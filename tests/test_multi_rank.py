@@ -185,6 +185,37 @@ def test_ranks_agree_on_the_time_seed(tmp_path):
         agree_on_seed(None, 1, 2)
 
 
+BAD_REFERENCE_WORKER = textwrap.dedent('''
+    import io, os, sys
+    sys.path.insert(0, %(root)r)
+    import torch.distributed as dist
+    from rustyread_b200 import simulate as S
+    rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+    dist.init_process_group("gloo")
+    try:
+        S.simulate(b"not a fasta file" if rank == 0 else None, "10x", io.BytesIO() if rank == 0 else None, dist=dist, rank=rank, world=world, seed=1,
+                   error_model="random", qscore_model="random", share_reference=True)
+        msg = "no error"
+    except RuntimeError as e:
+        msg = "RuntimeError: " + str(e)
+    open(os.path.join(%(out)r, "res_%%d" %% rank), "w").write(msg)
+    dist.destroy_process_group()
+''')
+
+
+def test_shared_reference_load_failure_reaches_every_rank(tmp_path):
+    """Rank 0 alone reads the reference; when that fails the other ranks get the error instead of waiting for a contig index."""
+    wpath = tmp_path / "bad.py"
+    wpath.write_text(BAD_REFERENCE_WORKER % dict(root=ROOT, out=str(tmp_path)))
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+           "--master-port", str(free_port()), str(wpath)]
+    r = subprocess.run(cmd, env=dict(os.environ, MASTER_ADDR="127.0.0.1"), capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    for i in range(2):
+        msg = (tmp_path / ("res_%d" % i)).read_text()
+        assert msg.startswith("RuntimeError: rank 0 could not load the reference") and "no sequence found" in msg, msg
+
+
 @pytest.mark.parametrize("parallel,world,chunk", [(False, 2, 10 ** 9), (True, 2, 10 ** 9), (True, 3, 40_000)])
 def test_world_size_2_simulate_matches_single_process(orc, tmp_path, parallel, world, chunk):
     """Single writer (shards gathered on rank 0) and parallel writer (every rank formats its shard and pwrites it at its
